@@ -1,0 +1,32 @@
+"""Core op interfaces of the paged-attention decoder hot path (the subset of the reference's
+``mojo_opset/core/__init__.py`` that ``BASELINE.json:north_star`` names)."""
+
+from .backend_registry import MojoBackendRegistry
+from .operator import MojoOperator
+from .operators.activation import MojoSilu
+from .operators.activation import MojoSwiGLU
+from .operators.attention import MojoPagedDecodeGQA
+from .operators.attention import MojoPagedPrefillGQA
+from .operators.attention import MojoSdpa
+from .operators.kv_cache import MojoStorePagedKVCache
+from .operators.kv_cache import build_paged_kv_chunk_metadata
+from .operators.normalization import MojoResidualAddRMSNorm
+from .operators.normalization import MojoRMSNorm
+from .operators.position_embedding import MojoApplyRoPE
+from .operators.position_embedding import MojoRotaryEmbedding
+
+__all__ = [
+    "MojoBackendRegistry",
+    "MojoOperator",
+    "MojoSilu",
+    "MojoSwiGLU",
+    "MojoPagedDecodeGQA",
+    "MojoPagedPrefillGQA",
+    "MojoSdpa",
+    "MojoStorePagedKVCache",
+    "build_paged_kv_chunk_metadata",
+    "MojoResidualAddRMSNorm",
+    "MojoRMSNorm",
+    "MojoApplyRoPE",
+    "MojoRotaryEmbedding",
+]
