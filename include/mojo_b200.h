@@ -1,0 +1,199 @@
+/*
+ * mojo_b200.h - C ABI of libmojo_b200.so, the B200 (sm_100a) kernels behind Mojo Opset's
+ * paged-attention decoder hot path.
+ *
+ * The reference (XPU-Forces/mojo_opset) is pure Python: a backend plugs in as a Python class per op
+ * (mojo_opset/core/backend_registry.py:48-91) whose forward() hands tensors to a kernel launcher.  The
+ * entry points below are what such a backend's launchers bind through ctypes - one per reference op
+ * forward, cited on each declaration.  INTEGRATION.md shows the Python-side stub.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes and element strides, no torch types;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*): no allocation, no
+ *     synchronisation, no host read of device data -> CUDA-graph capturable;
+ *   - return 0 on success, a negative MOJO_B200_E* code for a rejected request, or a positive
+ *     cudaError_t; mojo_b200_last_error() gives the message (thread local);
+ *   - `dtype` is a mojo_b200_dtype; strides are in ELEMENTS; the innermost (feature) dim is always
+ *     contiguous;
+ *   - there is no CPU path: without an sm_100 device the calls fail with the CUDA error.
+ */
+#ifndef MOJO_B200_H_
+#define MOJO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOJO_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MOJO_B200_API __attribute__((visibility("default")))
+#else
+#define MOJO_B200_API
+#endif
+
+typedef enum {
+  MOJO_B200_BF16 = 0,
+  MOJO_B200_F16 = 1,
+  MOJO_B200_F32 = 2
+} mojo_b200_dtype;
+
+enum {
+  MOJO_B200_OK = 0,
+  MOJO_B200_EINVAL = -1,       /* malformed argument (null pointer, negative size, misaligned stride) */
+  MOJO_B200_EUNSUPPORTED = -2, /* valid request this build has no kernel for -> NotImplementedError */
+  MOJO_B200_EWORKSPACE = -3    /* workspace too small */
+};
+
+MOJO_B200_API int mojo_b200_abi_version(void);
+MOJO_B200_API const char* mojo_b200_last_error(void);
+/* 1 if the current device is compute capability 10.x, 0 otherwise, <0 / >0 on error. */
+MOJO_B200_API int mojo_b200_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoStorePagedKVCache.forward                     mojo_opset/core/operators/kv_cache.py:110-171
+ *
+ * key_states/value_states [T, Hkv, D]  ->  key_cache/value_cache [NB, Hkv, bs, D]  (in place, bit exact)
+ * chunk plan rows: (src_token_start, dst_block_id, dst_block_offset, chunk_len), int32 [C, 4].
+ * Rows whose block id is outside [0, NB) or whose token range leaves [0, T) are skipped.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_store_paged_kv_chunks(
+    const void* key_states, const void* value_states, void* key_cache, void* value_cache,
+    const int32_t* chunk_metadata, int64_t num_chunks,
+    int64_t num_tokens, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size,
+    int64_t ks_stride_t, int64_t ks_stride_h, int64_t vs_stride_t, int64_t vs_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    int dtype, void* stream);
+
+/* Same op through the legacy (block_table, cu_q_lens | NULL, context_kv_lens) triple
+ * (kv_cache.py:142-150 + build_paged_kv_chunk_metadata :33-101) WITHOUT materialising the plan: one
+ * thread group per new token finds its sequence and slot on the device.  cu_q_lens == NULL is decode
+ * mode (one token per sequence, T == num_seqs). */
+MOJO_B200_API int mojo_b200_store_paged_kv_table(
+    const void* key_states, const void* value_states, void* key_cache, void* value_cache,
+    const int32_t* block_table, int64_t table_stride, int max_blocks_per_seq,
+    const int32_t* cu_q_lens, const int32_t* context_kv_lens, int num_seqs,
+    int64_t num_tokens, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size,
+    int64_t ks_stride_t, int64_t ks_stride_h, int64_t vs_stride_t, int64_t vs_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoRMSNorm.forward                               mojo_opset/core/operators/normalization.py:93-108
+ * MojoResidualAddRMSNorm.forward                    mojo_opset/core/operators/normalization.py:340-359
+ *
+ * rows x hidden, fp32 math, one rounding.  residual_add: sum = x + residual rounded to dtype first;
+ * sum_out may be NULL (norm_pos="post": only y is returned).  weight has the same dtype as x.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_rms_norm(const void* x, const void* weight, void* y, int64_t rows, int hidden,
+                       int64_t x_row_stride, int64_t y_row_stride, float eps, int dtype, void* stream);
+MOJO_B200_API int mojo_b200_residual_add_rms_norm(const void* x, const void* residual, const void* weight, void* y,
+                                    void* sum_out, int64_t rows, int hidden, int64_t x_row_stride,
+                                    int64_t res_row_stride, int64_t y_row_stride, int64_t sum_row_stride,
+                                    float eps, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoApplyRoPE.forward                             mojo_opset/core/operators/position_embedding.py:137-175
+ *
+ * Rotate-half on the LAST rope_dim features of every (batch, position, head) row of q and k.
+ * q/k are addressed as [batch, seq, heads, D] through strides, which covers [T,N,D], [N,T,D],
+ * [B,S,N,D] and [B,N,S,D] views alike; cos/sin as [batch, seq, rope_dim] (batch stride 0 to broadcast).
+ * cos_dtype == F32 with 16-bit q/k: fp32 math; cos_dtype == dtype: math in that dtype with every
+ * product and the sum rounded, as the eager golden does.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_apply_rope(const void* q, const void* k, const void* cos, const void* sin, void* q_out,
+                         void* k_out, int64_t batch, int64_t seq, int q_heads, int k_heads, int head_dim,
+                         int rope_dim,
+                         int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                         int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                         int64_t qo_stride_b, int64_t qo_stride_s, int64_t qo_stride_h,
+                         int64_t ko_stride_b, int64_t ko_stride_s, int64_t ko_stride_h,
+                         int64_t cos_stride_b, int64_t cos_stride_s, int dtype, int cos_dtype, void* stream);
+
+/* MojoRotaryEmbedding.forward                       mojo_opset/core/operators/position_embedding.py:43-95
+ * cos/sin [T, rope_dim] fp32 for T tokens.  Positions come from exactly one of
+ *   position_ids[T]                      (decode / explicit),
+ *   cu_q_lens[num_seqs+1] (+ optional total_seq_lens[num_seqs]: position = total - q_len + t), or
+ *   neither: position = token_index % period  (padded prefill, period = S).
+ * If table_cos/table_sin are non-NULL they are [table_rows, rope_dim] fp32 tables to gather from,
+ * otherwise angle = position * inv_freq[rope_dim/2] is evaluated in fp32 and scaled by attention_scaling. */
+MOJO_B200_API int mojo_b200_rotary_cos_sin(float* cos_out, float* sin_out, int64_t num_tokens, int rope_dim,
+                             const float* inv_freq, float attention_scaling,
+                             const int32_t* position_ids, const int32_t* cu_q_lens,
+                             const int32_t* total_seq_lens, int num_seqs, int64_t period,
+                             const float* table_cos, const float* table_sin, int64_t table_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoSwiGLU.forward / MojoSilu.forward             mojo_opset/core/operators/activation.py:43-63, :21-35
+ * [rows, cols] with per-tensor row strides (gate/up are often two halves of one fused projection).
+ * swiglu_limit > 0: up clamped to [-limit, limit], gate to <= limit first.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_swiglu(const void* gate, const void* up, void* out, int64_t rows, int64_t cols,
+                     int64_t gate_row_stride, int64_t up_row_stride, int64_t out_row_stride,
+                     float swiglu_limit, int dtype, void* stream);
+MOJO_B200_API int mojo_b200_silu(const void* x, void* out, int64_t rows, int64_t cols, int64_t x_row_stride,
+                   int64_t out_row_stride, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoPagedDecodeGQA.forward                        mojo_opset/core/operators/attention.py:141-229
+ *
+ * query [B, Hq, D] (strides b,h), caches [NB, Hkv, bs, D], total_seq_lens [B], block_tables [B, MB]
+ * (row stride table_stride) -> out [B, Hq, D].  Rows with seq_len <= 0 get zeros.  gqa_interleave: 0 =
+ * AABB (kv = h / G), 1 = ABAB (kv = h % Hkv).  Split-KV: `num_splits` partitions of each sequence's KV
+ * are reduced by a second kernel; the partials live in `workspace` (mojo_b200_paged_decode_workspace_bytes).
+ * num_splits <= 0 lets the library choose from (B, Hkv, max_seq_len); max_seq_len is a host-side hint
+ * (<= MB * bs), never read from the device.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_paged_decode_num_splits(int batch, int num_q_heads, int num_kv_heads, int head_dim,
+                                      int block_size, int64_t max_seq_len, int dtype);
+MOJO_B200_API size_t mojo_b200_paged_decode_workspace_bytes(int batch, int num_q_heads, int head_dim, int num_splits);
+MOJO_B200_API int mojo_b200_paged_decode_gqa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* total_seq_lens,
+    const int32_t* block_tables, void* out, void* workspace, size_t workspace_bytes,
+    int batch, int num_q_heads, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size,
+    int max_blocks_per_seq, int64_t table_stride, int64_t max_seq_len,
+    int64_t q_stride_b, int64_t q_stride_h, int64_t o_stride_b, int64_t o_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    float softmax_scale, int gqa_interleave, int num_splits, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoPagedPrefillGQA.forward                       mojo_opset/core/operators/attention.py:335-447
+ *
+ * query [T, Hq, D], cu_q_lens [B+1], cu_total_seq_lens [B+1] or NULL (kv_len = q_len), causal with offset
+ * kv_len - q_len.  max_q_len / max_kv_len are host-side hints used for grid sizing only.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_paged_prefill_gqa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* cu_q_lens,
+    const int32_t* cu_total_seq_lens, const int32_t* block_tables, void* out,
+    int64_t total_q_tokens, int batch, int num_q_heads, int num_kv_heads, int head_dim,
+    int64_t num_blocks, int block_size, int max_blocks_per_seq, int64_t table_stride,
+    int64_t max_q_len, int64_t max_kv_len,
+    int64_t q_stride_t, int64_t q_stride_h, int64_t o_stride_t, int64_t o_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    float softmax_scale, int gqa_interleave, int is_causal, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MojoSdpa.forward                                  mojo_opset/core/operators/attention.py:466-501
+ *
+ * query [B, Hq, Sq, D], key/value [B, Hkv, Skv, D] through (b, h, s) strides (D contiguous), no mask,
+ * non-causal, q head h -> kv head h / (Hq / Hkv).  out through its own strides.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_sdpa(const void* query, const void* key, const void* value, void* out,
+                   int batch, int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
+                   int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                   int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s,
+                   int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_s,
+                   int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
+                   float softmax_scale, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOJO_B200_H_ */

@@ -1,0 +1,25 @@
+"""``b200`` backend: ``B200<Op>`` classes subclassing the core ops (name prefix = backend key)."""
+
+from .operators.activation import B200Silu
+from .operators.activation import B200SwiGLU
+from .operators.attention import B200PagedDecodeGQA
+from .operators.attention import B200PagedPrefillGQA
+from .operators.attention import B200Sdpa
+from .operators.kv_cache import B200StorePagedKVCache
+from .operators.normalization import B200ResidualAddRMSNorm
+from .operators.normalization import B200RMSNorm
+from .operators.position_embedding import B200ApplyRoPE
+from .operators.position_embedding import B200RotaryEmbedding
+
+__all__ = [
+    "B200Silu",
+    "B200SwiGLU",
+    "B200PagedDecodeGQA",
+    "B200PagedPrefillGQA",
+    "B200Sdpa",
+    "B200StorePagedKVCache",
+    "B200ResidualAddRMSNorm",
+    "B200RMSNorm",
+    "B200ApplyRoPE",
+    "B200RotaryEmbedding",
+]

@@ -1,0 +1,126 @@
+// MojoSwiGLU / MojoSilu: flat element-wise, 128-bit accesses, one HBM pass (3 resp. 2 streams).
+//
+//   silu(g) = round_T(g / (1 + exp(-g)))            (fp32 math, IEEE division, accurate expf)
+//   swiglu  = round_T(silu(g) * u)                  (second rounding, as the eager golden: F.silu(g) * u)
+//
+// Rows may be strided (gate / up are commonly the two halves of one fused projection).  Grid: 2-D,
+// x over 16-byte vectors of a row, y over rows, sized so each thread issues 2 independent vector loads.
+#include "common.cuh"
+
+namespace mojo {
+
+__device__ __forceinline__ float silu_f(float g) { return __fdiv_rn(g, __fadd_rn(1.0f, expf(-g))); }
+
+// torch.clamp in the input dtype: NaN propagates, and a bound that is not representable in T is rounded
+// when it replaces a value (the eager op materialises its result in T).
+template <typename T> __device__ __forceinline__ void clamp_pair(float& gf, float& uf, float limit) {
+  if (uf == uf) uf = round_through<T>(fminf(fmaxf(uf, -limit), limit));
+  if (gf == gf) gf = round_through<T>(fminf(gf, limit));
+}
+
+template <typename T, bool GATED>
+__global__ void __launch_bounds__(256) act_kernel(const T* __restrict__ gate, const T* __restrict__ up,
+                                                  T* __restrict__ out, int64_t rows, int64_t cols, int64_t g_rs,
+                                                  int64_t u_rs, int64_t o_rs, float limit) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t vecs = cols / N;
+  for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+    const T* g = gate + row * g_rs;
+    const T* u = GATED ? up + row * u_rs : nullptr;
+    T* o = out + row * o_rs;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < vecs; v += (int64_t)gridDim.x * blockDim.x) {
+      const Vec16<T> gv = ld_vec_stream(g + v * N);
+      Vec16<T> uv;
+      if (GATED) uv = ld_vec_stream(u + v * N);
+      Vec16<T> ov;
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        float gf = DType<T>::to_f(gv.v[e]);
+        if (GATED) {
+          float uf = DType<T>::to_f(uv.v[e]);
+          if (limit > 0.f) clamp_pair<T>(gf, uf, limit);
+          ov.v[e] = DType<T>::from_f(__fmul_rn(round_through<T>(silu_f(gf)), uf));
+        } else {
+          ov.v[e] = DType<T>::from_f(silu_f(gf));
+        }
+      }
+      st_vec(o + v * N, ov);
+    }
+    // scalar tail when cols is not a multiple of the vector width
+    for (int64_t c = vecs * N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols;
+         c += (int64_t)gridDim.x * blockDim.x) {
+      float gf = DType<T>::to_f(g[c]);
+      if (GATED) {
+        float uf = DType<T>::to_f(u[c]);
+        if (limit > 0.f) clamp_pair<T>(gf, uf, limit);
+        o[c] = DType<T>::from_f(__fmul_rn(round_through<T>(silu_f(gf)), uf));
+      } else {
+        o[c] = DType<T>::from_f(silu_f(gf));
+      }
+    }
+  }
+}
+
+// scalar variant for rows whose strides / base pointers are not 16-byte aligned
+template <typename T, bool GATED>
+__global__ void __launch_bounds__(256) act_scalar_kernel(const T* __restrict__ gate, const T* __restrict__ up,
+                                                         T* __restrict__ out, int64_t rows, int64_t cols, int64_t g_rs,
+                                                         int64_t u_rs, int64_t o_rs, float limit) {
+  for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x) {
+      float gf = DType<T>::to_f(gate[row * g_rs + c]);
+      if (GATED) {
+        float uf = DType<T>::to_f(up[row * u_rs + c]);
+        if (limit > 0.f) clamp_pair<T>(gf, uf, limit);
+        out[row * o_rs + c] = DType<T>::from_f(__fmul_rn(round_through<T>(silu_f(gf)), uf));
+      } else {
+        out[row * o_rs + c] = DType<T>::from_f(silu_f(gf));
+      }
+    }
+  }
+}
+
+static int act_entry(const void* gate, const void* up, void* out, int64_t rows, int64_t cols, int64_t g_rs,
+                     int64_t u_rs, int64_t o_rs, float limit, int dtype, void* stream, bool gated) {
+  MOJO_REQUIRE(rows >= 0 && cols >= 0, MOJO_B200_EINVAL, "activation: bad sizes");
+  if (rows == 0 || cols == 0) return 0;
+  MOJO_REQUIRE(gate && out && (!gated || up), MOJO_B200_EINVAL, "activation: null tensor pointer");
+  const int eb = dtype_bytes(dtype);
+  const int n = 16 / eb;
+  const bool vec_ok = aligned16(gate) && aligned16(out) && (!gated || aligned16(up)) &&
+                      (rows == 1 || (g_rs % n == 0 && o_rs % n == 0 && (!gated || u_rs % n == 0)));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t per_row = vec_ok ? (cols + n - 1) / n : cols;
+  int64_t gx = (per_row + 256 * 2 - 1) / (256 * 2);
+  gx = gx < 1 ? 1 : (gx > 65535 ? 65535 : gx);
+  int64_t gy = rows;
+  const int64_t want = (int64_t)kNumSMs * 32;  // enough CTAs to fill the chip several waves deep
+  if (gx * gy > want * 4) gy = (want * 4 + gx - 1) / gx;
+  gy = gy < 1 ? 1 : (gy > 65535 ? 65535 : gy);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    if (vec_ok) {
+      if (gated) act_kernel<T, true><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
+      else act_kernel<T, false><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
+    } else {
+      if (gated) act_scalar_kernel<T, true><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
+      else act_scalar_kernel<T, false><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
+    }
+    return check_launch("act_kernel");
+  });
+}
+
+}  // namespace mojo
+
+extern "C" int mojo_b200_swiglu(const void* gate, const void* up, void* out, int64_t rows, int64_t cols,
+                                int64_t gate_row_stride, int64_t up_row_stride, int64_t out_row_stride,
+                                float swiglu_limit, int dtype, void* stream) {
+  return mojo::act_entry(gate, up, out, rows, cols, gate_row_stride, up_row_stride, out_row_stride, swiglu_limit, dtype,
+                         stream, true);
+}
+
+extern "C" int mojo_b200_silu(const void* x, void* out, int64_t rows, int64_t cols, int64_t x_row_stride,
+                              int64_t out_row_stride, int dtype, void* stream) {
+  return mojo::act_entry(x, nullptr, out, rows, cols, x_row_stride, 0, out_row_stride, 0.f, dtype, stream, false);
+}

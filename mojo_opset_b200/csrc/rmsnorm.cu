@@ -1,0 +1,185 @@
+// MojoRMSNorm / MojoResidualAddRMSNorm: one HBM pass, 128-bit accesses, fp32 math, one rounding.
+//
+//   sum = round_T(x + residual)                      (eager add materialises in the input dtype)
+//   y   = round_T(sum * (1 / sqrt(mean(sum^2) + eps)) * w)
+//
+// A row is owned by a group of TPR threads (a warp for head_dim-sized rows such as q/k-norm, a whole CTA
+// for hidden-sized rows).  Each thread keeps its slice of the row in registers between the reduction and
+// the scaling, so x / residual are read exactly once: bytes = (2 reads + 2 writes) * rows * H * sizeof(T) + H.
+#include "common.cuh"
+
+namespace mojo {
+
+constexpr int kMaxVecsPerThread = 4;  // register-resident slice: up to 4 x 16 B per thread
+
+template <typename T, int TPR, bool HAS_RES>
+__global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
+    const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, T* __restrict__ y,
+    T* __restrict__ sum_out, int64_t rows, int hidden, int64_t x_rs, int64_t res_rs, int64_t y_rs, int64_t sum_rs,
+    float eps) {
+  constexpr int N = Vec16<T>::N;
+  constexpr int ROWS_PER_CTA = (TPR >= 128 ? 1 : 128 / TPR);
+  const int lane_in_row = threadIdx.x % TPR;
+  const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + threadIdx.x / TPR;
+  const bool active = row < rows;
+  const int vecs = hidden / N;
+
+  Vec16<T> keep[kMaxVecsPerThread];
+  float ss = 0.f;
+  if (active) {
+    const T* xr = x + row * x_rs;
+    const T* rr = HAS_RES ? res + row * res_rs : nullptr;
+#pragma unroll
+    for (int i = 0; i < kMaxVecsPerThread; ++i) {
+      const int v = lane_in_row + i * TPR;
+      if (v < vecs) {
+        Vec16<T> a = ld_vec_stream(xr + (int64_t)v * N);
+        if (HAS_RES) {
+          const Vec16<T> b = ld_vec_stream(rr + (int64_t)v * N);
+#pragma unroll
+          for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
+          if (sum_out) st_vec(sum_out + row * sum_rs + (int64_t)v * N, a);
+        }
+        keep[i] = a;
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const float f = DType<T>::to_f(a.v[e]);
+          ss = fmaf(f, f, ss);
+        }
+      }
+    }
+    // rows wider than the register slice: stream the remainder (re-read in the second phase)
+    for (int v = lane_in_row + kMaxVecsPerThread * TPR; v < vecs; v += TPR) {
+      Vec16<T> a = ld_vec(xr + (int64_t)v * N);
+      if (HAS_RES) {
+        const Vec16<T> b = ld_vec(rr + (int64_t)v * N);
+#pragma unroll
+        for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
+        if (sum_out) st_vec(sum_out + row * sum_rs + (int64_t)v * N, a);
+      }
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float f = DType<T>::to_f(a.v[e]);
+        ss = fmaf(f, f, ss);
+      }
+    }
+  }
+
+  // reduce ss over the TPR threads of the row
+  if constexpr (TPR <= 32) {
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  } else {
+    __shared__ float part[32];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float t = (threadIdx.x < TPR / 32) ? part[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) {
+      t = warp_sum(t);
+      if (threadIdx.x == 0) part[0] = t;
+    }
+    __syncthreads();
+    ss = part[0];
+  }
+  if (!active) return;
+
+  const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)hidden), eps)));
+  T* yr = y + row * y_rs;
+#pragma unroll
+  for (int i = 0; i < kMaxVecsPerThread; ++i) {
+    const int v = lane_in_row + i * TPR;
+    if (v < vecs) {
+      const Vec16<T> g = ld_vec(w + (int64_t)v * N);
+      Vec16<T> o;
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        o.v[e] = DType<T>::from_f(__fmul_rn(__fmul_rn(DType<T>::to_f(keep[i].v[e]), inv), DType<T>::to_f(g.v[e])));
+      st_vec(yr + (int64_t)v * N, o);
+    }
+  }
+  for (int v = lane_in_row + kMaxVecsPerThread * TPR; v < vecs; v += TPR) {
+    // the summed row was either written to sum_out (re-read it) or must be recomputed from x (+ residual)
+    Vec16<T> a;
+    if (HAS_RES && sum_out) {
+      a = ld_vec(sum_out + row * sum_rs + (int64_t)v * N);
+    } else {
+      a = ld_vec(x + row * x_rs + (int64_t)v * N);
+      if (HAS_RES) {
+        const Vec16<T> b = ld_vec(res + row * res_rs + (int64_t)v * N);
+#pragma unroll
+        for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
+      }
+    }
+    const Vec16<T> g = ld_vec(w + (int64_t)v * N);
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < N; ++e)
+      o.v[e] = DType<T>::from_f(__fmul_rn(__fmul_rn(DType<T>::to_f(a.v[e]), inv), DType<T>::to_f(g.v[e])));
+    st_vec(yr + (int64_t)v * N, o);
+  }
+}
+
+template <typename T, bool HAS_RES>
+static int launch_rmsnorm(const void* x, const void* res, const void* w, void* y, void* sum_out, int64_t rows,
+                          int hidden, int64_t x_rs, int64_t res_rs, int64_t y_rs, int64_t sum_rs, float eps,
+                          cudaStream_t s) {
+  constexpr int N = Vec16<T>::N;
+  const int vecs = hidden / N;
+#define RUN(TPR)                                                                                              \
+  do {                                                                                                        \
+    constexpr int RPC = (TPR >= 128 ? 1 : 128 / TPR);                                                         \
+    const int64_t ctas = (rows + RPC - 1) / RPC;                                                              \
+    rmsnorm_kernel<T, TPR, HAS_RES><<<(unsigned)ctas, (TPR >= 128 ? TPR : 128), 0, s>>>(                      \
+        (const T*)x, (const T*)res, (const T*)w, (T*)y, (T*)sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, \
+        eps);                                                                                                 \
+  } while (0)
+  // pick the narrowest group that keeps the row register-resident (<= 4 vectors per thread)
+  if (vecs <= 8) RUN(8);
+  else if (vecs <= 32 * 2) RUN(32);
+  else if (vecs <= 128 * 2) RUN(128);
+  else if (vecs <= 256 * 2) RUN(256);
+  else if (vecs <= 512 * 4) RUN(512);
+  else RUN(1024);
+#undef RUN
+  return check_launch("rmsnorm_kernel");
+}
+
+static int rmsnorm_entry(const void* x, const void* res, const void* w, void* y, void* sum_out, int64_t rows,
+                         int hidden, int64_t x_rs, int64_t res_rs, int64_t y_rs, int64_t sum_rs, float eps, int dtype,
+                         void* stream, bool has_res) {
+  MOJO_REQUIRE(rows >= 0 && hidden > 0, MOJO_B200_EINVAL, "rms_norm: bad sizes rows=%lld hidden=%d", (long long)rows,
+               hidden);
+  if (rows == 0) return 0;
+  MOJO_REQUIRE(x && w && y && (!has_res || res), MOJO_B200_EINVAL, "rms_norm: null tensor pointer");
+  MOJO_REQUIRE(rows <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "rms_norm: too many rows");
+  const int eb = dtype_bytes(dtype);
+  const int n = 16 / eb;
+  const bool ok = hidden % n == 0 && x_rs % n == 0 && y_rs % n == 0 && (!has_res || res_rs % n == 0) &&
+                  (!sum_out || sum_rs % n == 0) && aligned16(x) && aligned16(w) && aligned16(y) &&
+                  (!has_res || aligned16(res)) && (!sum_out || aligned16(sum_out));
+  MOJO_REQUIRE(ok, MOJO_B200_EUNSUPPORTED,
+               "rms_norm: hidden size, row strides and base pointers must be multiples of 16 bytes (hidden=%d)", hidden);
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    return has_res ? launch_rmsnorm<T, true>(x, res, w, y, sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, eps, s)
+                   : launch_rmsnorm<T, false>(x, res, w, y, sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, eps, s);
+  });
+}
+
+}  // namespace mojo
+
+extern "C" int mojo_b200_rms_norm(const void* x, const void* weight, void* y, int64_t rows, int hidden,
+                                  int64_t x_row_stride, int64_t y_row_stride, float eps, int dtype, void* stream) {
+  return mojo::rmsnorm_entry(x, nullptr, weight, y, nullptr, rows, hidden, x_row_stride, 0, y_row_stride, 0, eps, dtype,
+                             stream, false);
+}
+
+extern "C" int mojo_b200_residual_add_rms_norm(const void* x, const void* residual, const void* weight, void* y,
+                                               void* sum_out, int64_t rows, int hidden, int64_t x_row_stride,
+                                               int64_t res_row_stride, int64_t y_row_stride, int64_t sum_row_stride,
+                                               float eps, int dtype, void* stream) {
+  return mojo::rmsnorm_entry(x, residual, weight, y, sum_out, rows, hidden, x_row_stride, res_row_stride, y_row_stride,
+                             sum_row_stride, eps, dtype, stream, true);
+}

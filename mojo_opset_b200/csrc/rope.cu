@@ -1,0 +1,223 @@
+// MojoApplyRoPE (rotate-half on the last rope_dim features of q and k, fused in one launch) and
+// MojoRotaryEmbedding (cos/sin rows for a batch of positions).
+//
+// apply_rope: q/k are addressed as [batch, seq, heads, D] through element strides, so token-first,
+// head-first and transposed-view layouts all take the same path.  One CTA per (batch, seq) token; its
+// threads sweep the (head, vector) space of q then k.  A work item is one VEC-wide slice of the first
+// rotary half together with its partner in the second half (both outputs produced by one thread), or one
+// pass-through slice of the leading non-rotary features.  bytes = 2 * T * (Nq+Nk) * D * sizeof(T) + 2*T*d*sizeof(cos).
+//
+// Rounding follows the eager golden: math in promote(T, cos dtype); each product and the sum are rounded
+// separately (no FMA contraction); when cos has the same 16-bit dtype as q the intermediates are rounded
+// to that dtype too.
+#include "common.cuh"
+
+namespace mojo {
+
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+
+template <typename T, typename C, int VEC, bool ROUND_T>
+__device__ __forceinline__ void rope_rows(const T* __restrict__ src, T* __restrict__ dst, int heads, int64_t s_h,
+                                          int64_t d_h, const C* __restrict__ cos, const C* __restrict__ sin,
+                                          int head_dim, int rope_dim) {
+  const int nope = head_dim - rope_dim;
+  const int half = rope_dim / 2;
+  const int nope_items = nope / VEC;
+  const int items = nope_items + half / VEC;
+  const int total = heads * items;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int h = i / items;
+    const int it = i - h * items;
+    const T* s = src + h * s_h;
+    T* d = dst + h * d_h;
+    if (it < nope_items) {
+      *reinterpret_cast<Pack<T, VEC>*>(d + it * VEC) = *reinterpret_cast<const Pack<T, VEC>*>(s + it * VEC);
+      continue;
+    }
+    const int r = (it - nope_items) * VEC;  // offset inside the first rotary half
+    const Pack<T, VEC> x1 = *reinterpret_cast<const Pack<T, VEC>*>(s + nope + r);
+    const Pack<T, VEC> x2 = *reinterpret_cast<const Pack<T, VEC>*>(s + nope + half + r);
+    const Pack<C, VEC> c1 = *reinterpret_cast<const Pack<C, VEC>*>(cos + r);
+    const Pack<C, VEC> c2 = *reinterpret_cast<const Pack<C, VEC>*>(cos + half + r);
+    const Pack<C, VEC> s1 = *reinterpret_cast<const Pack<C, VEC>*>(sin + r);
+    const Pack<C, VEC> s2 = *reinterpret_cast<const Pack<C, VEC>*>(sin + half + r);
+    Pack<T, VEC> o1, o2;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float a = DType<T>::to_f(x1.v[e]), b = DType<T>::to_f(x2.v[e]);
+      // first half:  x1*cos + (-x2)*sin ; second half: x2*cos + x1*sin
+      float p1 = __fmul_rn(a, DType<C>::to_f(c1.v[e])), q1 = __fmul_rn(-b, DType<C>::to_f(s1.v[e]));
+      float p2 = __fmul_rn(b, DType<C>::to_f(c2.v[e])), q2 = __fmul_rn(a, DType<C>::to_f(s2.v[e]));
+      if (ROUND_T) {
+        p1 = round_through<T>(p1); q1 = round_through<T>(q1);
+        p2 = round_through<T>(p2); q2 = round_through<T>(q2);
+      }
+      o1.v[e] = DType<T>::from_f(__fadd_rn(p1, q1));
+      o2.v[e] = DType<T>::from_f(__fadd_rn(p2, q2));
+    }
+    *reinterpret_cast<Pack<T, VEC>*>(d + nope + r) = o1;
+    *reinterpret_cast<Pack<T, VEC>*>(d + nope + half + r) = o2;
+  }
+}
+
+struct RopeArgs {
+  const void *q, *k, *cos, *sin;
+  void *qo, *ko;
+  int64_t seq;
+  int q_heads, k_heads, head_dim, rope_dim;
+  int64_t q_b, q_s, q_h, k_b, k_s, k_h, qo_b, qo_s, qo_h, ko_b, ko_s, ko_h, cos_b, cos_s;
+};
+
+template <typename T, typename C, int VEC, bool ROUND_T>
+__global__ void __launch_bounds__(256) apply_rope_kernel(const RopeArgs a) {
+  const int64_t tok = blockIdx.x;
+  const int64_t b = tok / a.seq;
+  const int64_t s = tok - b * a.seq;
+  const C* cos = (const C*)a.cos + b * a.cos_b + s * a.cos_s;
+  const C* sin = (const C*)a.sin + b * a.cos_b + s * a.cos_s;
+  rope_rows<T, C, VEC, ROUND_T>((const T*)a.q + b * a.q_b + s * a.q_s, (T*)a.qo + b * a.qo_b + s * a.qo_s, a.q_heads,
+                                a.q_h, a.qo_h, cos, sin, a.head_dim, a.rope_dim);
+  rope_rows<T, C, VEC, ROUND_T>((const T*)a.k + b * a.k_b + s * a.k_s, (T*)a.ko + b * a.ko_b + s * a.ko_s, a.k_heads,
+                                a.k_h, a.ko_h, cos, sin, a.head_dim, a.rope_dim);
+}
+
+template <typename T, typename C, bool ROUND_T>
+static int launch_rope(const RopeArgs& a, int64_t tokens, int vec, cudaStream_t s) {
+  const int64_t work = (int64_t)(a.q_heads + a.k_heads) * ((a.head_dim - a.rope_dim / 2) / vec);
+  int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
+  switch (vec) {
+    case 8: apply_rope_kernel<T, C, (sizeof(T) == 2 ? 8 : 4), ROUND_T><<<(unsigned)tokens, threads, 0, s>>>(a); break;
+    case 4: apply_rope_kernel<T, C, 4, ROUND_T><<<(unsigned)tokens, threads, 0, s>>>(a); break;
+    case 2: apply_rope_kernel<T, C, 2, ROUND_T><<<(unsigned)tokens, threads, 0, s>>>(a); break;
+    default: apply_rope_kernel<T, C, 1, ROUND_T><<<(unsigned)tokens, threads, 0, s>>>(a); break;
+  }
+  return check_launch("apply_rope_kernel");
+}
+
+// positions -> cos/sin rows
+__global__ void __launch_bounds__(128) rotary_cos_sin_kernel(
+    float* __restrict__ cos_out, float* __restrict__ sin_out, int64_t num_tokens, int rope_dim,
+    const float* __restrict__ inv_freq, float scaling, const int32_t* __restrict__ position_ids,
+    const int32_t* __restrict__ cu_q, const int32_t* __restrict__ total_lens, int num_seqs, int64_t period,
+    const float* __restrict__ table_cos, const float* __restrict__ table_sin, int64_t table_rows) {
+  const int64_t tok = blockIdx.x;
+  int64_t pos;
+  if (position_ids) {
+    pos = position_ids[tok];
+  } else if (cu_q) {
+    int lo = 0, hi = num_seqs + 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cu_q[mid] <= tok) lo = mid + 1; else hi = mid;
+    }
+    const int seq = lo - 1;
+    if (seq < 0 || seq >= num_seqs) {
+      pos = -1;  // token outside every sequence keeps the reference's -1 position
+    } else {
+      const int q_len = cu_q[seq + 1] - cu_q[seq];
+      const int ctx = total_lens ? total_lens[seq] - q_len : 0;
+      pos = ctx + (tok - cu_q[seq]);
+    }
+  } else {
+    pos = tok % period;
+  }
+  const int half = rope_dim / 2;
+  float* c = cos_out + tok * rope_dim;
+  float* s = sin_out + tok * rope_dim;
+  if (table_cos) {
+    // python-style negative index wraps once; anything still outside the table yields zeros
+    int64_t row = pos < 0 ? pos + table_rows : pos;
+    const bool ok = row >= 0 && row < table_rows;
+    for (int i = threadIdx.x; i < rope_dim; i += blockDim.x) {
+      c[i] = ok ? table_cos[row * rope_dim + i] : 0.f;
+      s[i] = ok ? table_sin[row * rope_dim + i] : 0.f;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float ang = __fmul_rn((float)pos, inv_freq[i]);
+    float sv, cv;
+    sincosf(ang, &sv, &cv);
+    cv = __fmul_rn(cv, scaling);
+    sv = __fmul_rn(sv, scaling);
+    c[i] = cv; c[i + half] = cv;
+    s[i] = sv; s[i + half] = sv;
+  }
+}
+
+}  // namespace mojo
+
+extern "C" int mojo_b200_apply_rope(const void* q, const void* k, const void* cos, const void* sin, void* q_out,
+                                    void* k_out, int64_t batch, int64_t seq, int q_heads, int k_heads, int head_dim,
+                                    int rope_dim, int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                                    int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h, int64_t qo_stride_b,
+                                    int64_t qo_stride_s, int64_t qo_stride_h, int64_t ko_stride_b, int64_t ko_stride_s,
+                                    int64_t ko_stride_h, int64_t cos_stride_b, int64_t cos_stride_s, int dtype,
+                                    int cos_dtype, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(batch >= 0 && seq >= 0 && q_heads >= 0 && k_heads >= 0 && head_dim > 0, MOJO_B200_EINVAL,
+               "apply_rope: bad sizes");
+  MOJO_REQUIRE(rope_dim >= 0 && rope_dim <= head_dim && rope_dim % 2 == 0, MOJO_B200_EINVAL,
+               "apply_rope: rope_dim %d must be even and <= head_dim %d", rope_dim, head_dim);
+  const int64_t tokens = batch * seq;
+  if (tokens == 0 || q_heads + k_heads == 0) return 0;
+  MOJO_REQUIRE(q && k && cos && sin && q_out && k_out, MOJO_B200_EINVAL, "apply_rope: null tensor pointer");
+  MOJO_REQUIRE(tokens <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "apply_rope: too many tokens");
+  MOJO_REQUIRE(dtype >= 0 && dtype <= 2 && cos_dtype >= 0 && cos_dtype <= 2, MOJO_B200_EINVAL, "apply_rope: bad dtype");
+
+  RopeArgs a{q, k, cos, sin, q_out, k_out, seq, q_heads, k_heads, head_dim, rope_dim,
+             q_stride_b, q_stride_s, q_stride_h, k_stride_b, k_stride_s, k_stride_h,
+             qo_stride_b, qo_stride_s, qo_stride_h, ko_stride_b, ko_stride_s, ko_stride_h, cos_stride_b, cos_stride_s};
+
+  // widest power-of-two element vector every offset, stride and base pointer allows (16 bytes max for T)
+  const int eb = dtype_bytes(dtype), cb = dtype_bytes(cos_dtype);
+  const int half = rope_dim / 2, nope = head_dim - rope_dim;
+  int vec = 16 / eb;
+  auto fits = [&](int v) {
+    if (half % v || nope % v) return false;
+    const int64_t strides[] = {q_stride_b, q_stride_s, q_stride_h, k_stride_b, k_stride_s, k_stride_h,
+                               qo_stride_b, qo_stride_s, qo_stride_h, ko_stride_b, ko_stride_s, ko_stride_h,
+                               cos_stride_b, cos_stride_s};
+    for (int64_t st : strides) if (st % v) return false;
+    const uintptr_t tb = (uintptr_t)v * eb - 1, cbm = (uintptr_t)v * cb - 1;
+    if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)q_out | (uintptr_t)k_out) & tb) return false;
+    if (((uintptr_t)cos | (uintptr_t)sin) & cbm) return false;
+    return true;
+  };
+  while (vec > 1 && !fits(vec)) vec >>= 1;
+
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool round_t = (cos_dtype == dtype) && dtype != MOJO_B200_F32;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using T = decltype(tt);
+    return dispatch_dtype(cos_dtype, [&](auto ct) {
+      using C = decltype(ct);
+      if constexpr (sizeof(T) == 2 && std::is_same<T, C>::value) {
+        return launch_rope<T, C, true>(a, tokens, vec, s);
+      } else {
+        (void)round_t;
+        return launch_rope<T, C, false>(a, tokens, vec, s);
+      }
+    });
+  });
+}
+
+extern "C" int mojo_b200_rotary_cos_sin(float* cos_out, float* sin_out, int64_t num_tokens, int rope_dim,
+                                        const float* inv_freq, float attention_scaling, const int32_t* position_ids,
+                                        const int32_t* cu_q_lens, const int32_t* total_seq_lens, int num_seqs,
+                                        int64_t period, const float* table_cos, const float* table_sin,
+                                        int64_t table_rows, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(num_tokens >= 0 && rope_dim > 0 && rope_dim % 2 == 0, MOJO_B200_EINVAL, "rotary: bad sizes");
+  if (num_tokens == 0) return 0;
+  MOJO_REQUIRE(cos_out && sin_out, MOJO_B200_EINVAL, "rotary: null output");
+  MOJO_REQUIRE((table_cos && table_sin && table_rows > 0) || inv_freq, MOJO_B200_EINVAL,
+               "rotary: need inv_freq or a cos/sin table");
+  MOJO_REQUIRE(!(position_ids && cu_q_lens), MOJO_B200_EINVAL, "rotary: position_ids and cu_q_lens are exclusive");
+  MOJO_REQUIRE(position_ids || cu_q_lens || period > 0, MOJO_B200_EINVAL, "rotary: period must be > 0");
+  MOJO_REQUIRE(num_tokens <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "rotary: too many tokens");
+  rotary_cos_sin_kernel<<<(unsigned)num_tokens, 128, 0, (cudaStream_t)stream>>>(
+      cos_out, sin_out, num_tokens, rope_dim, inv_freq, attention_scaling, position_ids, cu_q_lens, total_seq_lens,
+      num_seqs, period, table_cos, table_sin, table_rows);
+  return check_launch("rotary_cos_sin_kernel");
+}

@@ -1,0 +1,148 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the registry
+dispatches like the reference's, the b200 ops refuse to run without a GPU, host-side argument logic."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mojo_b200.h")).read()
+    return sorted(set(re.findall(r"MOJO_B200_API\s+[\w\s\*]+?\b(mojo_b200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mojo_opset_b200 import _lib
+    from mojo_opset_b200.build import build
+
+    build()  # no-op when up to date; nvcc cross-compiles without a GPU
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 16
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mojo_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.SIGNATURES"
+    assert set(_lib.SIGNATURES) == set(declared)
+    lib.mojo_b200_abi_version.restype = ctypes.c_int
+    assert lib.mojo_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """On a box without an sm_100 GPU the product refuses to compute instead of falling back."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU box")
+    import mojo_opset_b200 as m
+    from mojo_opset_b200 import functional as F
+    from mojo_opset_b200.backends.b200 import B200PagedDecodeGQA
+    from mojo_opset_b200.backends.b200 import B200SwiGLU
+
+    assert "b200" not in m.MojoSwiGLU.get_registered_backends()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200SwiGLU()(torch.randn(8), torch.randn(8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F.rms_norm(torch.randn(2, 8), torch.randn(8), 1e-6)
+    q = torch.randn(1, 4, 64)
+    kc = torch.randn(2, 1, 16, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200PagedDecodeGQA()(q, kc, kc, torch.tensor([3], dtype=torch.int32), torch.zeros(1, 1, dtype=torch.int32))
+
+
+def test_product_does_not_import_oracle():
+    code = (
+        "import sys; import mojo_opset_b200, mojo_opset_b200.functional, mojo_opset_b200.backends.b200;"
+        "assert not any(n == 'oracle' or n.startswith('oracle.') for n in sys.modules), 'oracle imported by product'"
+    )
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mojo_opset_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+
+
+def test_registry_dispatch(torch_backend):
+    """Reference tests/base/test_backend_dispatch.py:12-44, restated for the b200/torch pair."""
+    import mojo_opset_b200 as m
+
+    reg = m.MojoSilu.get_registry()
+    assert reg is m.MojoSilu._registry
+    torch_cls = m.MojoSilu.get_backend_impl("torch")
+    assert torch_cls is reg.get("torch") and torch_cls.__name__ == "TorchSilu"
+    assert reg.get(" Torch ") is torch_cls
+    assert type(m.MojoSilu()) is m.MojoSilu.get_backend_impl()
+    with pytest.raises(KeyError):
+        m.MojoSilu.get_backend_impl("ttx", strict=True)
+    assert m.MojoSilu.get_backend_impl("ttx") is m.MojoSilu.get_backend_impl()  # silent fallback, like upstream
+    op = m.MojoPagedDecodeGQA(gqa_layout="ABAB")
+    assert op.gqa_layout == "ABAB" and op.is_causal
+    with pytest.raises(ValueError):
+        m.MojoPagedDecodeGQA(gqa_layout="ABBA")
+    with pytest.raises(NotImplementedError):
+        op.forward_diff_with(m.MojoPagedDecodeGQA(gqa_layout="ABAB"))
+
+
+def test_registration_rules():
+    import mojo_opset_b200 as m
+
+    with pytest.raises(AssertionError):
+
+        class TTXSilu(m.MojoSilu):  # unknown backend prefix
+            pass
+
+    with pytest.raises(NameError):
+
+        class B200xSilu(m.MojoSilu):  # typo of a known prefix
+            pass
+
+
+def test_b200_registers_on_platform():
+    code = (
+        "import os; os.environ['MOJO_BACKEND']='b200';"
+        "import mojo_opset_b200 as m;"
+        "ops=[m.MojoPagedDecodeGQA,m.MojoPagedPrefillGQA,m.MojoSdpa,m.MojoStorePagedKVCache,m.MojoResidualAddRMSNorm,"
+        "m.MojoRMSNorm,m.MojoApplyRoPE,m.MojoRotaryEmbedding,m.MojoSwiGLU,m.MojoSilu];"
+        "assert all(o.get_registered_backends()==('b200',) for o in ops);"
+        "assert type(m.MojoSdpa()).__name__=='B200Sdpa' and type(m.MojoSdpa()).__base__ is m.MojoSdpa;"
+        "import oracle.torch_backend;"
+        "assert m.MojoSdpa.get_registered_backends()==('b200','torch');"
+        "os.environ['MOJO_BACKEND']='torch'; assert type(m.MojoSdpa()).__name__=='TorchSdpa'"
+    )
+    env = dict(os.environ, MOJO_PLATFORM="b200")
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT, env=env)
+
+
+def test_contracts_raise_like_reference():
+    from mojo_opset_b200.backends.b200 import B200ApplyRoPE
+    from mojo_opset_b200.backends.b200 import B200PagedDecodeGQA
+    from mojo_opset_b200.backends.b200 import B200PagedPrefillGQA
+    from mojo_opset_b200.backends.b200 import B200Sdpa
+    from mojo_opset_b200.backends.b200 import B200StorePagedKVCache
+
+    q = torch.randn(2, 4, 64)
+    kc = torch.randn(4, 1, 16, 64)
+    lens64 = torch.tensor([3, 4])  # int64: contract violation
+    tables = torch.zeros(2, 1, dtype=torch.int32)
+    with pytest.raises(AssertionError):
+        B200PagedDecodeGQA()(q, kc, kc, lens64, tables)
+    with pytest.raises(NotImplementedError):
+        B200PagedDecodeGQA()(q, kc, kc, lens64.int(), tables, mask=torch.ones(4, 4, dtype=torch.bool))
+    with pytest.raises(NotImplementedError):
+        B200PagedDecodeGQA(is_causal=False)(q, kc, kc, lens64.int(), tables)
+    with pytest.raises(AssertionError):  # cu_total_seq_lens must be cumulative [B+1]
+        B200PagedPrefillGQA()(q, kc, kc, torch.tensor([0, 1, 2], dtype=torch.int32), tables, None,
+                              torch.tensor([3, 4], dtype=torch.int32))
+    with pytest.raises(NotImplementedError):
+        B200Sdpa()(q[None], q[None], q[None], attn_mask=torch.ones(4, 4, dtype=torch.bool))
+    with pytest.raises(AssertionError):  # mixing the plan with the legacy triple
+        B200StorePagedKVCache()(q, q, kc, kc, tables, chunk_metadata=torch.zeros(1, 4, dtype=torch.int32))
+    with pytest.raises(AssertionError):
+        B200ApplyRoPE()(q, q[None], torch.randn(2, 64), torch.randn(2, 64))
+    with pytest.raises(AssertionError):
+        B200ApplyRoPE(interleaved=True)
