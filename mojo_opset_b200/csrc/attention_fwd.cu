@@ -1,15 +1,458 @@
-// MojoPagedPrefillGQA / MojoSdpa entry points (placeholder until the tensor-core kernels land).
-#include "common.cuh"
+// MojoPagedPrefillGQA (var-len causal attention over a paged KV cache) and MojoSdpa (dense non-causal
+// attention over strided [B,H,S,D] views): FlashAttention-2 style forward on mma.sync tensor-core tiles.
+//
+// This is the general path of the two ops: any 16-bit dtype, D in {64,128}, any power-of-two page size >= 8,
+// ragged sequences, cached prefixes, GQA in both layouts.  (The tcgen05/TMEM kernel in attention_fwd_sm100.cu
+// takes the shapes it is specialised for; the entry points below pick.)
+//
+//   grid  (q tiles of 64 rows [heaviest first], Hq, B); 160 threads = 4 consumer warps (16 query rows each) +
+//         1 TMA producer warp; 2 CTAs/SM.
+//   K/V   64-token tiles through a full/empty mbarrier ring, one TMA tensor copy per (page, K|V); a dense
+//         tensor is addressed as "one page per batch element" by the same 5-D tensor map.
+//   math  S = Q K^T (fp32 accumulate) -> [paged prefill: rounded to the input dtype, as the golden's einsum]
+//         -> * scale -> causal / length mask -> online softmax (log2 domain) -> P rounded to the input dtype
+//         -> O += P V (fp32) -> O / l.
+// FLOPs = 4 * D * (number of unmasked (q, k) pairs) per query head.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 
-extern "C" int mojo_b200_paged_prefill_gqa(
-    const void*, const void*, const void*, const int32_t*, const int32_t*, const int32_t*, void*, int64_t, int, int,
-    int, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-    int64_t, int64_t, int64_t, int64_t, float, int, int, int, void*) {
-  return mojo::fail(MOJO_B200_EUNSUPPORTED, "paged_prefill_gqa: kernel not built yet");
+#include "tma.cuh"
+
+namespace mojo {
+
+constexpr int kAttnConsumerWarps = 4;
+constexpr int kAttnThreads = 32 * (kAttnConsumerWarps + 1);
+constexpr int kBM = 16 * kAttnConsumerWarps;  // query rows per CTA
+constexpr float kLog2eF = 1.4426950408889634f;
+
+struct AttnParams {
+  const void* q;
+  void* out;
+  const int32_t* cu_q;    // paged: [B+1]
+  const int32_t* cu_kv;   // paged: [B+1] or null
+  const int32_t* tables;  // paged: [B, MB]
+  int64_t table_stride;
+  int max_blocks, block_size, log2_bs, box_rows;
+  int num_q_heads, num_kv_heads, group;
+  int64_t q_len_dense, kv_len_dense;
+  int64_t q_st, q_sh, q_sb, o_st, o_sh, o_sb;
+  float scale_log2;  // softmax_scale * log2(e)
+  int interleave, causal, dense, stages, round_scores;
+};
+
+template <typename T, int D, bool SPLIT_HALVES>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_constant__ CUtensorMap v_map,
+                    const AttnParams p) {
+  constexpr int NH = D / 64;
+  constexpr int KS = D / 16;
+  constexpr int TILE_BYTES = kTile * D * 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stages = p.stages;
+  uint8_t* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * 2 * TILE_BYTES);
+  uint64_t* empty = full + stages;
+
+  const int b = blockIdx.z;
+  const int hq = blockIdx.y;
+  const int q_tile = gridDim.x - 1 - blockIdx.x;  // causal: the longest rows start first
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int64_t q_start;
+  int q_len, kv_len;
+  if (p.dense) {
+    q_start = 0;
+    q_len = (int)p.q_len_dense;
+    kv_len = (int)p.kv_len_dense;
+  } else {
+    q_start = p.cu_q[b];
+    q_len = p.cu_q[b + 1] - (int)q_start;
+    kv_len = p.cu_kv ? p.cu_kv[b + 1] - p.cu_kv[b] : q_len;
+  }
+  const int m0 = q_tile * kBM;
+  if (m0 >= q_len || kv_len <= 0) return;
+  const int off = kv_len - q_len;  // query row t sees keys 0 .. off + t
+  const int last_row = min(m0 + kBM, q_len) - 1;
+  const int n_end = p.causal ? min(kv_len, off + last_row + 1) : kv_len;
+  const int n_tiles = n_end > 0 ? (n_end + kTile - 1) / kTile : 0;
+  if (n_tiles == 0) return;  // rows that see no key keep the zeros the output was initialised with
+  const int kvh = p.interleave ? hq % p.num_kv_heads : hq / p.group;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kAttnConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int box_rows = p.box_rows;
+  const int boxes_per_tile = kTile / box_rows;
+
+  if (warp == kAttnConsumerWarps) {
+    // ------------------------------------------------------------------ producer warp
+    if (lane == 0) {
+      tma_prefetch_desc(&k_map);
+      tma_prefetch_desc(&v_map);
+    }
+    const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
+    const uint32_t box_bytes = (uint32_t)box_rows * D * 2;
+    for (int it = 0; it < n_tiles; ++it) {
+      const int stage = it % stages;
+      const uint32_t phase = (uint32_t)(it / stages) & 1u;
+      const int tok0 = it * kTile;
+      const int want = min(boxes_per_tile, (kv_len - tok0 + box_rows - 1) / box_rows);
+      int blk = 0, row_in_page = 0;
+      if (lane < want) {
+        const int tok = tok0 + lane * box_rows;
+        if (p.dense) {
+          blk = b;
+          row_in_page = tok;
+        } else {
+          const int page = tok >> p.log2_bs;
+          row_in_page = tok & (p.block_size - 1);
+          blk = page < p.max_blocks ? table[page] : -1;
+        }
+      }
+      if (lane == 0) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_expect_tx(&full[stage], 2u * box_bytes * (uint32_t)want);
+      }
+      __syncwarp();
+      if (lane < want) {
+        uint8_t* kdst = tiles + (size_t)stage * 2 * TILE_BYTES + (size_t)lane * box_bytes;
+        uint8_t* vdst = kdst + TILE_BYTES;
+        if (SPLIT_HALVES) {
+          tma_load_5d(kdst, &k_map, &full[stage], 0, row_in_page, 0, kvh, blk);
+          tma_load_5d(vdst, &v_map, &full[stage], 0, row_in_page, 0, kvh, blk);
+        } else {
+          tma_load_5d(kdst, &k_map, &full[stage], 0, 0, row_in_page, kvh, blk);
+          tma_load_5d(vdst, &v_map, &full[stage], 0, 0, row_in_page, kvh, blk);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  const int g = lane >> 2, c = lane & 3;
+  const int row_lo = m0 + warp * 16 + g, row_hi = row_lo + 8;  // rows inside the sequence
+
+  uint32_t qf[KS][4];
+  {
+    const T* qb = reinterpret_cast<const T*>(p.q) + (int64_t)b * p.q_sb + (int64_t)hq * p.q_sh;
+    const T* r0 = row_lo < q_len ? qb + (q_start + row_lo) * p.q_st : nullptr;
+    const T* r1 = row_hi < q_len ? qb + (q_start + row_hi) * p.q_st : nullptr;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int d0 = ks * 16 + 2 * c;
+      qf[ks][0] = r0 ? *reinterpret_cast<const uint32_t*>(r0 + d0) : 0u;
+      qf[ks][1] = r1 ? *reinterpret_cast<const uint32_t*>(r1 + d0) : 0u;
+      qf[ks][2] = r0 ? *reinterpret_cast<const uint32_t*>(r0 + d0 + 8) : 0u;
+      qf[ks][3] = r1 ? *reinterpret_cast<const uint32_t*>(r1 + d0 + 8) : 0u;
+    }
+  }
+
+  float o[2 * KS][4];
+#pragma unroll
+  for (int i = 0; i < 2 * KS; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+  const int mat = lane >> 3, mr = lane & 7;
+  auto line_of = [&](int row, int half) -> uint32_t {
+    if (SPLIT_HALVES) {
+      const int box = row / box_rows, r = row - box * box_rows;
+      return (uint32_t)(box * box_rows * NH + half * box_rows + r);
+    }
+    return (uint32_t)(row * NH + half);
+  };
+  // last key each of this thread's two rows may see
+  const int lim_lo = p.causal ? min(kv_len - 1, off + row_lo) : kv_len - 1;
+  const int lim_hi = p.causal ? min(kv_len - 1, off + row_hi) : kv_len - 1;
+  const int warp_first_lim = p.causal ? off + m0 + warp * 16 : kv_len - 1;       // most restrictive row
+  const int warp_last_lim = p.causal ? off + m0 + warp * 16 + 15 : kv_len - 1;   // least restrictive row
+  const float scale_log2 = p.scale_log2;
+  const bool round_scores = p.round_scores != 0;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int stage = it % stages;
+    const uint32_t phase = (uint32_t)(it / stages) & 1u;
+    const int n0 = it * kTile;
+    uint8_t* sk = tiles + (size_t)stage * 2 * TILE_BYTES;
+    uint8_t* sv = sk + TILE_BYTES;
+    const uint32_t sk_a = smem_u32(sk), sv_a = smem_u32(sv);
+
+    mbar_wait(&full[stage], phase);
+
+    if (n0 <= warp_last_lim) {  // otherwise none of this warp's rows sees the tile (causal)
+      const int valid = kv_len - n0;
+      if (valid < kTile) {
+        // tail tile: zero the V rows past the end of the sequence (every warp reads all 64 rows, and each
+        // zeroes them itself, so no cross-warp ordering is needed - all writers store zeros)
+        for (int r = valid + (lane >> 1); r < kTile; r += 16) {
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            uint4* dst = reinterpret_cast<uint4*>(sv + line_of(r, h) * 128u + (lane & 1) * 64);
+            dst[0] = dst[1] = dst[2] = dst[3] = make_uint4(0, 0, 0, 0);
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- S = Q K^T : 16 rows x 64 keys
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          const int row = np * 16 + (mat >> 1) * 8 + mr;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(sk_a + swz128(line_of(row, ks >> 2), ((ks * 2) & 7) + (mat & 1)), b0, b1, b2, b3);
+          Mma16816<T>::run(s[2 * np], qf[ks], b0, b1);
+          Mma16816<T>::run(s[2 * np + 1], qf[ks], b2, b3);
+        }
+      }
+
+      // ---- rounding, scale, mask
+      const bool need_mask = n0 + kTile - 1 > warp_first_lim || valid < kTile;
+      float tile_lo = -INFINITY, tile_hi = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v = round_scores ? round_through<T>(s[j][e]) : s[j][e];
+          v *= scale_log2;
+          if (need_mask) {
+            const int key = n0 + j * 8 + 2 * c + (e & 1);
+            if (key > (e < 2 ? lim_lo : lim_hi)) v = -INFINITY;
+          }
+          s[j][e] = v;
+          if (e < 2) tile_lo = fmaxf(tile_lo, v); else tile_hi = fmaxf(tile_hi, v);
+        }
+      }
+      tile_lo = fmaxf(tile_lo, __shfl_xor_sync(0xffffffffu, tile_lo, 1));
+      tile_lo = fmaxf(tile_lo, __shfl_xor_sync(0xffffffffu, tile_lo, 2));
+      tile_hi = fmaxf(tile_hi, __shfl_xor_sync(0xffffffffu, tile_hi, 1));
+      tile_hi = fmaxf(tile_hi, __shfl_xor_sync(0xffffffffu, tile_hi, 2));
+      const float new_lo = fmaxf(m_lo, tile_lo), new_hi = fmaxf(m_hi, tile_hi);
+      const float base_lo = new_lo == -INFINITY ? 0.f : new_lo, base_hi = new_hi == -INFINITY ? 0.f : new_hi;
+      const float a_lo = exp2f(m_lo - base_lo), a_hi = exp2f(m_hi - base_hi);
+      m_lo = new_lo;
+      m_hi = new_hi;
+      float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = exp2f(s[j][0] - base_lo);
+        s[j][1] = exp2f(s[j][1] - base_lo);
+        s[j][2] = exp2f(s[j][2] - base_hi);
+        s[j][3] = exp2f(s[j][3] - base_hi);
+        sum_lo += s[j][0] + s[j][1];
+        sum_hi += s[j][2] + s[j][3];
+      }
+      l_lo = l_lo * a_lo + sum_lo;
+      l_hi = l_hi * a_hi + sum_hi;
+#pragma unroll
+      for (int i = 0; i < 2 * KS; ++i) {
+        o[i][0] *= a_lo;
+        o[i][1] *= a_lo;
+        o[i][2] *= a_hi;
+        o[i][3] *= a_hi;
+      }
+
+      // ---- O += P V
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = Mma16816<T>::pack(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = Mma16816<T>::pack(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = Mma16816<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = Mma16816<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int row = kk * 16 + (mat & 1) * 8 + mr;
+#pragma unroll
+        for (int dp = 0; dp < KS; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(sv_a + swz128(line_of(row, dp >> 2), ((dp * 2) & 7) + (mat >> 1)), b0, b1, b2, b3);
+          Mma16816<T>::run(o[2 * dp], pa, b0, b1);
+          Mma16816<T>::run(o[2 * dp + 1], pa, b2, b3);
+        }
+      }
+    }
+
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+  }
+
+  // -------------------------------------------------------------------- epilogue: O / l -> out
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float inv_lo = l_lo > 0.f ? 1.f / l_lo : 0.f, inv_hi = l_hi > 0.f ? 1.f / l_hi : 0.f;
+  T* ob = reinterpret_cast<T*>(p.out) + (int64_t)b * p.o_sb + (int64_t)hq * p.o_sh;
+  if (row_lo < q_len) {
+    T* dst = ob + (q_start + row_lo) * p.o_st;
+#pragma unroll
+    for (int i = 0; i < 2 * KS; ++i)
+      *reinterpret_cast<uint32_t*>(dst + i * 8 + 2 * c) = Mma16816<T>::pack(o[i][0] * inv_lo, o[i][1] * inv_lo);
+  }
+  if (row_hi < q_len) {
+    T* dst = ob + (q_start + row_hi) * p.o_st;
+#pragma unroll
+    for (int i = 0; i < 2 * KS; ++i)
+      *reinterpret_cast<uint32_t*>(dst + i * 8 + 2 * c) = Mma16816<T>::pack(o[i][2] * inv_hi, o[i][3] * inv_hi);
+  }
 }
 
-extern "C" int mojo_b200_sdpa(const void*, const void*, const void*, void*, int, int, int, int64_t, int64_t, int,
-                              int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                              int64_t, int64_t, int64_t, float, int, void*) {
-  return mojo::fail(MOJO_B200_EUNSUPPORTED, "sdpa: kernel not built yet");
+// ------------------------------------------------------------------------------------------------------
+static int attn_env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : fallback;
+}
+
+struct KvDesc {
+  const void* k;
+  const void* v;
+  int64_t k_b, k_h, k_t, v_b, v_h, v_t;  // element strides: block|batch, head, token
+  int64_t rows_per_block;                // page size, or kv_len for a dense tensor
+  int64_t num_blocks;                    // pages, or batch for a dense tensor
+  int num_kv_heads;
+};
+
+static int launch_attn_mma(const KvDesc& kv, AttnParams& p, int head_dim, int dtype, dim3 grid, cudaStream_t s) {
+  const int64_t strides[] = {kv.k_b, kv.k_h, kv.k_t, kv.v_b, kv.v_h, kv.v_t};
+  for (int64_t st : strides)
+    MOJO_REQUIRE(st > 0 && st % 8 == 0, MOJO_B200_EUNSUPPORTED,
+                 "attention: K/V strides must be positive multiples of 8 elements (TMA), got %lld", (long long)st);
+  MOJO_REQUIRE(aligned16(kv.k) && aligned16(kv.v), MOJO_B200_EUNSUPPORTED, "attention: K/V base must be 16-byte aligned");
+  MOJO_REQUIRE(((p.q_st | p.q_sh | p.q_sb | p.o_st | p.o_sh | p.o_sb) % 2) == 0 && ((uintptr_t)p.q & 3) == 0 &&
+                   ((uintptr_t)p.out & 3) == 0,
+               MOJO_B200_EUNSUPPORTED, "attention: q/out strides must be even and bases 4-byte aligned");
+
+  const int tile_bytes = kTile * head_dim * 2;
+  int stages = attn_env_int("MOJO_B200_ATTN_STAGES", 0);
+  if (stages <= 0) stages = head_dim == 128 ? 3 : 6;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * 2 * tile_bytes + 2 * stages * sizeof(uint64_t) + 1024;
+
+  const char* layout = getenv("MOJO_B200_DECODE_LAYOUT");
+  bool split_halves = head_dim == 128 && !(layout && !strcmp(layout, "natural"));
+  CUtensorMap k_map, v_map;
+  int rc = build_cache_map(kv.k, dtype, head_dim, kv.rows_per_block, kv.num_kv_heads, kv.num_blocks, kv.k_b, kv.k_h,
+                           kv.k_t, split_halves, p.box_rows, &k_map);
+  if (rc != 0 && split_halves && !(layout && !strcmp(layout, "split"))) {
+    split_halves = false;
+    rc = build_cache_map(kv.k, dtype, head_dim, kv.rows_per_block, kv.num_kv_heads, kv.num_blocks, kv.k_b, kv.k_h,
+                         kv.k_t, false, p.box_rows, &k_map);
+  }
+  if (rc != 0) return rc;
+  rc = build_cache_map(kv.v, dtype, head_dim, kv.rows_per_block, kv.num_kv_heads, kv.num_blocks, kv.v_b, kv.v_h, kv.v_t,
+                       split_halves, p.box_rows, &v_map);
+  if (rc != 0) return rc;
+
+#define LAUNCH_ATTN(TT, DD, SH)                                                                          \
+  do {                                                                                                   \
+    auto kern = attn_fwd_mma_kernel<TT, DD, SH>;                                                         \
+    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    kern<<<grid, kAttnThreads, smem, s>>>(k_map, v_map, p);                                              \
+  } while (0)
+  if (dtype == MOJO_B200_BF16) {
+    if (head_dim == 128) { if (split_halves) LAUNCH_ATTN(__nv_bfloat16, 128, true); else LAUNCH_ATTN(__nv_bfloat16, 128, false); }
+    else LAUNCH_ATTN(__nv_bfloat16, 64, false);
+  } else {
+    if (head_dim == 128) { if (split_halves) LAUNCH_ATTN(__half, 128, true); else LAUNCH_ATTN(__half, 128, false); }
+    else LAUNCH_ATTN(__half, 64, false);
+  }
+#undef LAUNCH_ATTN
+  return check_launch("attn_fwd_mma_kernel");
+}
+
+}  // namespace mojo
+
+extern "C" int mojo_b200_paged_prefill_gqa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* cu_q_lens,
+    const int32_t* cu_total_seq_lens, const int32_t* block_tables, void* out, int64_t total_q_tokens, int batch,
+    int num_q_heads, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq,
+    int64_t table_stride, int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h,
+    int64_t o_stride_t, int64_t o_stride_h, int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t, float softmax_scale, int gqa_interleave,
+    int is_causal, int dtype, void* stream) {
+  using namespace mojo;
+  (void)max_kv_len;
+  MOJO_REQUIRE(total_q_tokens >= 0 && batch >= 0 && num_q_heads > 0 && num_kv_heads > 0 && head_dim > 0 &&
+                   block_size > 0 && max_blocks_per_seq >= 0 && num_blocks >= 0,
+               MOJO_B200_EINVAL, "paged_prefill: bad sizes");
+  MOJO_REQUIRE(num_q_heads % num_kv_heads == 0, MOJO_B200_EINVAL, "paged_prefill: Hq %d not a multiple of Hkv %d",
+               num_q_heads, num_kv_heads);
+  if (total_q_tokens == 0 || batch == 0 || max_blocks_per_seq == 0 || num_blocks == 0) return 0;
+  MOJO_REQUIRE(query && key_cache && value_cache && cu_q_lens && block_tables && out, MOJO_B200_EINVAL,
+               "paged_prefill: null tensor pointer");
+  MOJO_REQUIRE(is_causal, MOJO_B200_EUNSUPPORTED, "paged_prefill: only causal attention is built");
+  MOJO_REQUIRE(dtype == MOJO_B200_BF16 || dtype == MOJO_B200_F16, MOJO_B200_EUNSUPPORTED,
+               "paged_prefill: bf16/fp16 only (tensor-core path)");
+  MOJO_REQUIRE(head_dim == 64 || head_dim == 128, MOJO_B200_EUNSUPPORTED, "paged_prefill: head_dim %d not in {64,128}",
+               head_dim);
+  MOJO_REQUIRE(block_size >= 8 && (block_size & (block_size - 1)) == 0, MOJO_B200_EUNSUPPORTED,
+               "paged_prefill: block_size %d must be a power of two >= 8", block_size);
+  MOJO_REQUIRE(batch <= 65535 && num_q_heads <= 65535, MOJO_B200_EUNSUPPORTED, "paged_prefill: grid too large");
+  if (max_q_len <= 0 || max_q_len > total_q_tokens) max_q_len = total_q_tokens;
+
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = query; p.out = out; p.cu_q = cu_q_lens; p.cu_kv = cu_total_seq_lens; p.tables = block_tables;
+  p.table_stride = table_stride; p.max_blocks = max_blocks_per_seq; p.block_size = block_size;
+  while ((1 << p.log2_bs) < block_size) ++p.log2_bs;
+  p.box_rows = block_size < kTile ? block_size : kTile;
+  p.num_q_heads = num_q_heads; p.num_kv_heads = num_kv_heads; p.group = num_q_heads / num_kv_heads;
+  p.q_st = q_stride_t; p.q_sh = q_stride_h; p.q_sb = 0; p.o_st = o_stride_t; p.o_sh = o_stride_h; p.o_sb = 0;
+  p.scale_log2 = softmax_scale * kLog2eF;
+  p.interleave = gqa_interleave ? 1 : 0; p.causal = 1; p.dense = 0; p.round_scores = 1;
+
+  KvDesc kv{key_cache, value_cache, kc_stride_b, kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t,
+            block_size, num_blocks, num_kv_heads};
+  dim3 grid((unsigned)((max_q_len + kBM - 1) / kBM), (unsigned)num_q_heads, (unsigned)batch);
+  return launch_attn_mma(kv, p, head_dim, dtype, grid, (cudaStream_t)stream);
+}
+
+extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* value, void* out, int batch,
+                              int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
+                              int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s, int64_t k_stride_b,
+                              int64_t k_stride_h, int64_t k_stride_s, int64_t v_stride_b, int64_t v_stride_h,
+                              int64_t v_stride_s, int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
+                              float softmax_scale, int dtype, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(batch >= 0 && num_q_heads > 0 && num_kv_heads > 0 && q_len >= 0 && kv_len >= 0 && head_dim > 0,
+               MOJO_B200_EINVAL, "sdpa: bad sizes");
+  MOJO_REQUIRE(num_q_heads % num_kv_heads == 0, MOJO_B200_EINVAL, "sdpa: Hq %d not a multiple of Hkv %d", num_q_heads,
+               num_kv_heads);
+  if (batch == 0 || q_len == 0) return 0;
+  MOJO_REQUIRE(kv_len > 0, MOJO_B200_EINVAL, "sdpa: kv_len must be > 0");
+  MOJO_REQUIRE(query && key && value && out, MOJO_B200_EINVAL, "sdpa: null tensor pointer");
+  MOJO_REQUIRE(dtype == MOJO_B200_BF16 || dtype == MOJO_B200_F16, MOJO_B200_EUNSUPPORTED,
+               "sdpa: bf16/fp16 only (tensor-core path)");
+  MOJO_REQUIRE(head_dim == 64 || head_dim == 128, MOJO_B200_EUNSUPPORTED, "sdpa: head_dim %d not in {64,128}", head_dim);
+  MOJO_REQUIRE(batch <= 65535 && num_q_heads <= 65535 && q_len < (1LL << 31) && kv_len < (1LL << 31),
+               MOJO_B200_EUNSUPPORTED, "sdpa: shape too large");
+
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = query; p.out = out;
+  p.box_rows = kTile;
+  p.num_q_heads = num_q_heads; p.num_kv_heads = num_kv_heads; p.group = num_q_heads / num_kv_heads;
+  p.q_len_dense = q_len; p.kv_len_dense = kv_len;
+  p.q_st = q_stride_s; p.q_sh = q_stride_h; p.q_sb = q_stride_b;
+  p.o_st = o_stride_s; p.o_sh = o_stride_h; p.o_sb = o_stride_b;
+  p.scale_log2 = softmax_scale * kLog2eF;
+  p.interleave = 0; p.causal = 0; p.dense = 1; p.round_scores = 0;
+
+  KvDesc kv{key, value, k_stride_b, k_stride_h, k_stride_s, v_stride_b, v_stride_h, v_stride_s, kv_len, batch,
+            num_kv_heads};
+  dim3 grid((unsigned)((q_len + kBM - 1) / kBM), (unsigned)num_q_heads, (unsigned)batch);
+  return launch_attn_mma(kv, p, head_dim, dtype, grid, (cudaStream_t)stream);
 }

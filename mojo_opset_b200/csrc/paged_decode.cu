@@ -27,7 +27,6 @@
 
 namespace mojo {
 
-constexpr int kTile = 64;  // tokens per pipeline stage / split granularity
 constexpr int kConsumerWarps = 4;
 constexpr int kDecodeThreads = 32 * (kConsumerWarps + 1);
 constexpr float kLog2e = 1.4426950408889634f;
@@ -517,31 +516,6 @@ static bool fast_path_ok(int dtype, int head_dim, int block_size, const void* q,
   return env_int("MOJO_B200_DECODE_FORCE_SIMT", 0) == 0;
 }
 
-static int build_cache_map(const void* base, int dtype, int head_dim, int block_size, int num_kv_heads,
-                           int64_t num_blocks, int64_t s_b, int64_t s_h, int64_t s_t, bool split_halves,
-                           CUtensorMap* out) {
-  const int nh = head_dim / 64;
-  const int box_rows = block_size < kTile ? block_size : kTile;
-  TensorMapKey key;
-  memset(&key, 0, sizeof(key));
-  key.base = base;
-  key.rank = 5;
-  key.dtype = dtype;
-  key.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
-  key.dims[0] = 64;
-  key.box[0] = 64;
-  if (split_halves) {  // [64 | token | half | head | block]: a box lands as [half][token][128 B]
-    key.dims[1] = (uint64_t)block_size; key.strides[0] = (uint64_t)s_t * 2; key.box[1] = (uint32_t)box_rows;
-    key.dims[2] = (uint64_t)nh;         key.strides[1] = 128;               key.box[2] = (uint32_t)nh;
-  } else {             // [64 | half | token | head | block]: a box lands as [token][half][128 B]
-    key.dims[1] = (uint64_t)nh;         key.strides[0] = 128;               key.box[1] = (uint32_t)nh;
-    key.dims[2] = (uint64_t)block_size; key.strides[1] = (uint64_t)s_t * 2; key.box[2] = (uint32_t)box_rows;
-  }
-  key.dims[3] = (uint64_t)num_kv_heads; key.strides[2] = (uint64_t)s_h * 2; key.box[3] = 1;
-  key.dims[4] = (uint64_t)num_blocks;   key.strides[3] = (uint64_t)s_b * 2; key.box[4] = 1;
-  return get_tensor_map(key, out);
-}
-
 static int choose_splits(int batch, int num_kv_heads, int head_tiles, int64_t max_seq_len) {
   const int forced = env_int("MOJO_B200_DECODE_SPLITS", 0);
   if (forced > 0) return forced;
@@ -658,16 +632,17 @@ extern "C" int mojo_b200_paged_decode_gqa(
     const char* layout = getenv("MOJO_B200_DECODE_LAYOUT");
     bool split_halves = head_dim == 128 && !(layout && !strcmp(layout, "natural"));
     CUtensorMap k_map, v_map;
+    const int box_rows = block_size < kTile ? block_size : kTile;
     int rc = build_cache_map(key_cache, dtype, head_dim, block_size, num_kv_heads, num_blocks, kc_stride_b, kc_stride_h,
-                             kc_stride_t, split_halves, &k_map);
+                             kc_stride_t, split_halves, box_rows, &k_map);
     if (rc != 0 && split_halves && !(layout && !strcmp(layout, "split"))) {
       split_halves = false;  // driver rejected the permuted strides: natural order (2-way ldmatrix conflicts)
       rc = build_cache_map(key_cache, dtype, head_dim, block_size, num_kv_heads, num_blocks, kc_stride_b, kc_stride_h,
-                           kc_stride_t, false, &k_map);
+                           kc_stride_t, false, box_rows, &k_map);
     }
     if (rc != 0) return rc;
     rc = build_cache_map(value_cache, dtype, head_dim, block_size, num_kv_heads, num_blocks, vc_stride_b, vc_stride_h,
-                         vc_stride_t, split_halves, &v_map);
+                         vc_stride_t, split_halves, box_rows, &v_map);
     if (rc != 0) return rc;
 
 #define LAUNCH_FAST(TT, DD, SH)                                                                          \

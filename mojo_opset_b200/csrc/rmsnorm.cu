@@ -12,19 +12,29 @@ namespace mojo {
 
 constexpr int kMaxVecsPerThread = 4;  // register-resident slice: up to 4 x 16 B per thread
 
-template <typename T, int TPR, bool HAS_RES>
+// VEC elements per access: 16 bytes when the hidden size, strides and pointers allow, narrower otherwise
+// (e.g. hidden = 7338 or 734 in the reference's tests is only 4-byte divisible in 16-bit dtypes).
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) PackN { T v[VEC]; };
+template <typename T, int VEC> __device__ __forceinline__ PackN<T, VEC> ld_pack(const T* p) {
+  return *reinterpret_cast<const PackN<T, VEC>*>(p);
+}
+template <typename T, int VEC> __device__ __forceinline__ void st_pack(T* p, const PackN<T, VEC>& v) {
+  *reinterpret_cast<PackN<T, VEC>*>(p) = v;
+}
+
+template <typename T, int VEC, int TPR, bool HAS_RES>
 __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
     const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, T* __restrict__ y,
     T* __restrict__ sum_out, int64_t rows, int hidden, int64_t x_rs, int64_t res_rs, int64_t y_rs, int64_t sum_rs,
     float eps) {
-  constexpr int N = Vec16<T>::N;
+  constexpr int N = VEC;
   constexpr int ROWS_PER_CTA = (TPR >= 128 ? 1 : 128 / TPR);
   const int lane_in_row = threadIdx.x % TPR;
   const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + threadIdx.x / TPR;
   const bool active = row < rows;
   const int vecs = hidden / N;
 
-  Vec16<T> keep[kMaxVecsPerThread];
+  PackN<T, VEC> keep[kMaxVecsPerThread];
   float ss = 0.f;
   if (active) {
     const T* xr = x + row * x_rs;
@@ -33,12 +43,12 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
     for (int i = 0; i < kMaxVecsPerThread; ++i) {
       const int v = lane_in_row + i * TPR;
       if (v < vecs) {
-        Vec16<T> a = ld_vec_stream(xr + (int64_t)v * N);
+        PackN<T, VEC> a = ld_pack<T, VEC>(xr + (int64_t)v * N);
         if (HAS_RES) {
-          const Vec16<T> b = ld_vec_stream(rr + (int64_t)v * N);
+          const PackN<T, VEC> b = ld_pack<T, VEC>(rr + (int64_t)v * N);
 #pragma unroll
           for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
-          if (sum_out) st_vec(sum_out + row * sum_rs + (int64_t)v * N, a);
+          if (sum_out) st_pack<T, VEC>(sum_out + row * sum_rs + (int64_t)v * N, a);
         }
         keep[i] = a;
 #pragma unroll
@@ -50,12 +60,12 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
     }
     // rows wider than the register slice: stream the remainder (re-read in the second phase)
     for (int v = lane_in_row + kMaxVecsPerThread * TPR; v < vecs; v += TPR) {
-      Vec16<T> a = ld_vec(xr + (int64_t)v * N);
+      PackN<T, VEC> a = ld_pack<T, VEC>(xr + (int64_t)v * N);
       if (HAS_RES) {
-        const Vec16<T> b = ld_vec(rr + (int64_t)v * N);
+        const PackN<T, VEC> b = ld_pack<T, VEC>(rr + (int64_t)v * N);
 #pragma unroll
         for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
-        if (sum_out) st_vec(sum_out + row * sum_rs + (int64_t)v * N, a);
+        if (sum_out) st_pack<T, VEC>(sum_out + row * sum_rs + (int64_t)v * N, a);
       }
 #pragma unroll
       for (int e = 0; e < N; ++e) {
@@ -90,51 +100,50 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
   for (int i = 0; i < kMaxVecsPerThread; ++i) {
     const int v = lane_in_row + i * TPR;
     if (v < vecs) {
-      const Vec16<T> g = ld_vec(w + (int64_t)v * N);
-      Vec16<T> o;
+      const PackN<T, VEC> g = ld_pack<T, VEC>(w + (int64_t)v * N);
+      PackN<T, VEC> o;
 #pragma unroll
       for (int e = 0; e < N; ++e)
         o.v[e] = DType<T>::from_f(__fmul_rn(__fmul_rn(DType<T>::to_f(keep[i].v[e]), inv), DType<T>::to_f(g.v[e])));
-      st_vec(yr + (int64_t)v * N, o);
+      st_pack<T, VEC>(yr + (int64_t)v * N, o);
     }
   }
   for (int v = lane_in_row + kMaxVecsPerThread * TPR; v < vecs; v += TPR) {
     // the summed row was either written to sum_out (re-read it) or must be recomputed from x (+ residual)
-    Vec16<T> a;
+    PackN<T, VEC> a;
     if (HAS_RES && sum_out) {
-      a = ld_vec(sum_out + row * sum_rs + (int64_t)v * N);
+      a = ld_pack<T, VEC>(sum_out + row * sum_rs + (int64_t)v * N);
     } else {
-      a = ld_vec(x + row * x_rs + (int64_t)v * N);
+      a = ld_pack<T, VEC>(x + row * x_rs + (int64_t)v * N);
       if (HAS_RES) {
-        const Vec16<T> b = ld_vec(res + row * res_rs + (int64_t)v * N);
+        const PackN<T, VEC> b = ld_pack<T, VEC>(res + row * res_rs + (int64_t)v * N);
 #pragma unroll
         for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
       }
     }
-    const Vec16<T> g = ld_vec(w + (int64_t)v * N);
-    Vec16<T> o;
+    const PackN<T, VEC> g = ld_pack<T, VEC>(w + (int64_t)v * N);
+    PackN<T, VEC> o;
 #pragma unroll
     for (int e = 0; e < N; ++e)
       o.v[e] = DType<T>::from_f(__fmul_rn(__fmul_rn(DType<T>::to_f(a.v[e]), inv), DType<T>::to_f(g.v[e])));
-    st_vec(yr + (int64_t)v * N, o);
+    st_pack<T, VEC>(yr + (int64_t)v * N, o);
   }
 }
 
-template <typename T, bool HAS_RES>
+template <typename T, int VEC, bool HAS_RES>
 static int launch_rmsnorm(const void* x, const void* res, const void* w, void* y, void* sum_out, int64_t rows,
                           int hidden, int64_t x_rs, int64_t res_rs, int64_t y_rs, int64_t sum_rs, float eps,
                           cudaStream_t s) {
-  constexpr int N = Vec16<T>::N;
-  const int vecs = hidden / N;
+  const int vecs = hidden / VEC;
 #define RUN(TPR)                                                                                              \
   do {                                                                                                        \
     constexpr int RPC = (TPR >= 128 ? 1 : 128 / TPR);                                                         \
     const int64_t ctas = (rows + RPC - 1) / RPC;                                                              \
-    rmsnorm_kernel<T, TPR, HAS_RES><<<(unsigned)ctas, (TPR >= 128 ? TPR : 128), 0, s>>>(                      \
+    rmsnorm_kernel<T, VEC, TPR, HAS_RES><<<(unsigned)ctas, (TPR >= 128 ? TPR : 128), 0, s>>>(                 \
         (const T*)x, (const T*)res, (const T*)w, (T*)y, (T*)sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, \
         eps);                                                                                                 \
   } while (0)
-  // pick the narrowest group that keeps the row register-resident (<= 4 vectors per thread)
+  // pick the narrowest group that keeps the row register-resident (<= 4 packs per thread)
   if (vecs <= 8) RUN(8);
   else if (vecs <= 32 * 2) RUN(32);
   else if (vecs <= 128 * 2) RUN(128);
@@ -154,17 +163,31 @@ static int rmsnorm_entry(const void* x, const void* res, const void* w, void* y,
   MOJO_REQUIRE(x && w && y && (!has_res || res), MOJO_B200_EINVAL, "rms_norm: null tensor pointer");
   MOJO_REQUIRE(rows <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "rms_norm: too many rows");
   const int eb = dtype_bytes(dtype);
-  const int n = 16 / eb;
-  const bool ok = hidden % n == 0 && x_rs % n == 0 && y_rs % n == 0 && (!has_res || res_rs % n == 0) &&
-                  (!sum_out || sum_rs % n == 0) && aligned16(x) && aligned16(w) && aligned16(y) &&
-                  (!has_res || aligned16(res)) && (!sum_out || aligned16(sum_out));
-  MOJO_REQUIRE(ok, MOJO_B200_EUNSUPPORTED,
-               "rms_norm: hidden size, row strides and base pointers must be multiples of 16 bytes (hidden=%d)", hidden);
+  // widest power-of-two pack (<= 16 bytes) that the hidden size, every row stride and base pointer allow
+  int vec = 16 / eb;
+  auto fits = [&](int v) {
+    if (hidden % v || x_rs % v || y_rs % v || (has_res && res_rs % v) || (sum_out && sum_rs % v)) return false;
+    const uintptr_t m = (uintptr_t)v * eb - 1;
+    uintptr_t bits = (uintptr_t)x | (uintptr_t)w | (uintptr_t)y;
+    if (has_res) bits |= (uintptr_t)res;
+    if (sum_out) bits |= (uintptr_t)sum_out;
+    return (bits & m) == 0;
+  };
+  while (vec > 1 && !fits(vec)) vec >>= 1;
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_dtype(dtype, [&](auto tag) {
     using T = decltype(tag);
-    return has_res ? launch_rmsnorm<T, true>(x, res, w, y, sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, eps, s)
-                   : launch_rmsnorm<T, false>(x, res, w, y, sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, eps, s);
+    constexpr int kMaxVec = 16 / (int)sizeof(T);
+#define GO(V)                                                                                                      \
+  (has_res ? launch_rmsnorm<T, V, true>(x, res, w, y, sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, eps, s)   \
+           : launch_rmsnorm<T, V, false>(x, res, w, y, sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, eps, s))
+    if constexpr (kMaxVec >= 8) {
+      if (vec == 8) return GO(8);
+    }
+    if (vec >= 4) return GO(4);
+    if (vec == 2) return GO(2);
+    return GO(1);
+#undef GO
   });
 }
 

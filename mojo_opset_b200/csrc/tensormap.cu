@@ -91,4 +91,29 @@ int get_tensor_map(const TensorMapKey& key, CUtensorMap* out) {
   return 0;
 }
 
+int build_cache_map(const void* base, int dtype, int head_dim, int64_t block_size, int num_kv_heads,
+                    int64_t num_blocks, int64_t s_b, int64_t s_h, int64_t s_t, bool split_halves, int box_rows,
+                    CUtensorMap* out) {
+  const int nh = head_dim / 64;
+  TensorMapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = 5;
+  key.dtype = dtype;
+  key.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  key.dims[0] = 64;
+  key.box[0] = 64;
+  if (split_halves) {  // [64 | token | half | head | block]: a box lands as [half][token][128 B]
+    key.dims[1] = (uint64_t)block_size; key.strides[0] = (uint64_t)s_t * 2; key.box[1] = (uint32_t)box_rows;
+    key.dims[2] = (uint64_t)nh;         key.strides[1] = 128;               key.box[2] = (uint32_t)nh;
+  } else {             // [64 | half | token | head | block]: a box lands as [token][half][128 B]
+    key.dims[1] = (uint64_t)nh;         key.strides[0] = 128;               key.box[1] = (uint32_t)nh;
+    key.dims[2] = (uint64_t)block_size; key.strides[1] = (uint64_t)s_t * 2; key.box[2] = (uint32_t)box_rows;
+  }
+  key.dims[3] = (uint64_t)num_kv_heads; key.strides[2] = (uint64_t)s_h * 2; key.box[3] = 1;
+  key.dims[4] = (uint64_t)num_blocks;   key.strides[3] = (uint64_t)s_b * 2; key.box[4] = 1;
+  return get_tensor_map(key, out);
+}
+
+
 }  // namespace mojo

@@ -136,4 +136,18 @@ struct TensorMapKey {
 // Returns 0 and fills *out (a copy of a cached 128-byte descriptor) or an error code (+ last_error).
 int get_tensor_map(const TensorMapKey& key, CUtensorMap* out);
 
+// KV tiles are staged 64 tokens at a time by every attention kernel.
+constexpr int kTile = 64;
+
+// 5-D tensor map over a [blocks, heads, tokens, D] cache (element strides s_b, s_h, s_t; D contiguous, 16-bit
+// elements, D a multiple of 64) whose box is `box_rows` token rows of one (block, head); rows past the end
+// of a block are zero filled by the TMA unit:
+//   split_halves = false: dims [64 | D/64 | token | head | block] -> a box lands as [token][half][128 B]
+//   split_halves = true : dims [64 | token | D/64 | head | block] -> a box lands as [half][token][128 B]
+// Both use the 128-byte swizzle; the second keeps ldmatrix conflict free for D = 128.
+// A dense [B, H, S, D] tensor is the same thing with block = batch and block_size = S.
+int build_cache_map(const void* base, int dtype, int head_dim, int64_t block_size, int num_kv_heads,
+                    int64_t num_blocks, int64_t s_b, int64_t s_h, int64_t s_t, bool split_halves, int box_rows,
+                    CUtensorMap* out);
+
 }  // namespace mojo
