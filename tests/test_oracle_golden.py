@@ -95,3 +95,16 @@ def test_rotary_embedding_bit_exact(case):
 def test_activation_bit_exact(case):
     assert torch.equal(golden.swiglu(case["gate"], case["up"], case["swiglu_limit"]), case["out"])
     assert torch.equal(golden.silu(case["gate"]), case["silu_out"])
+
+
+@pytest.mark.parametrize("case", STORE, ids=_ids(STORE))
+def test_c_oracle_store_kv_bit_exact(case):
+    """The plain-C restatement (oracle/store_kv.c) against the reference's vectors."""
+    from oracle import store_kv_c
+
+    bs = case["key_cache"].shape[2]
+    plan = store_kv_c.build_chunk_plan(case["block_table"], case["cu_q_lens"], case["context_kv_lens"], bs)
+    assert torch.equal(plan, case["chunk_metadata"])
+    kc = store_kv_c.store_paged_kv(case["key_states"].contiguous(), case["key_cache"].clone(), plan)
+    vc = store_kv_c.store_paged_kv(case["value_states"].contiguous(), case["value_cache"].clone(), plan)
+    assert torch.equal(kc, case["key_cache_out"]) and torch.equal(vc, case["value_cache_out"])
