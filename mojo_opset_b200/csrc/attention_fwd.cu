@@ -3,7 +3,7 @@
 //
 // This is the general path of the two ops: any 16-bit dtype, D in {64,128}, any power-of-two page size >= 8,
 // ragged sequences, cached prefixes, GQA in both layouts.  (The tcgen05/TMEM kernel in attention_fwd_sm100.cu
-// takes the shapes it is specialised for; the entry points below pick.)
+// takes the shapes it is specialised for - head_dim 128, query chunks of >= 192 rows; the entry points below pick.)
 //
 //   grid  (q tiles of 64 rows [heaviest first], Hq, B); 160 threads = 4 consumer warps (16 query rows each) +
 //         1 TMA producer warp; 2 CTAs/SM.
@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "attention_sm100.cuh"
 #include "tma.cuh"
 
 namespace mojo {
@@ -403,6 +404,22 @@ extern "C" int mojo_b200_paged_prefill_gqa(
   MOJO_REQUIRE(batch <= 65535 && num_q_heads <= 65535, MOJO_B200_EUNSUPPORTED, "paged_prefill: grid too large");
   if (max_q_len <= 0 || max_q_len > total_q_tokens) max_q_len = total_q_tokens;
 
+  {  // tcgen05/TMEM kernel when the shape is covered
+    AttnSm100Args a;
+    memset(&a, 0, sizeof(a));
+    a.q = query; a.out = out; a.q_rows = total_q_tokens; a.q_st = q_stride_t; a.q_sh = q_stride_h;
+    a.o_st = o_stride_t; a.o_sh = o_stride_h;
+    a.k = key_cache; a.v = value_cache; a.k_b = kc_stride_b; a.k_h = kc_stride_h; a.k_t = kc_stride_t;
+    a.v_b = vc_stride_b; a.v_h = vc_stride_h; a.v_t = vc_stride_t;
+    a.rows_per_block = block_size; a.num_blocks = num_blocks;
+    a.cu_q = cu_q_lens; a.cu_kv = cu_total_seq_lens; a.tables = block_tables; a.table_stride = table_stride;
+    a.max_blocks = max_blocks_per_seq; a.batch = batch; a.num_q_heads = num_q_heads; a.num_kv_heads = num_kv_heads;
+    a.head_dim = head_dim; a.max_q_len = max_q_len; a.softmax_scale = softmax_scale;
+    a.interleave = gqa_interleave ? 1 : 0; a.causal = 1; a.dense = 0; a.round_scores = 1; a.dtype = dtype;
+    const int rc = launch_attn_sm100(a, (cudaStream_t)stream);
+    if (rc != kAttnNotEligible) return rc;
+  }
+
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = query; p.out = out; p.cu_q = cu_q_lens; p.cu_kv = cu_total_seq_lens; p.tables = block_tables;
@@ -439,6 +456,21 @@ extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* va
   MOJO_REQUIRE(head_dim == 64 || head_dim == 128, MOJO_B200_EUNSUPPORTED, "sdpa: head_dim %d not in {64,128}", head_dim);
   MOJO_REQUIRE(batch <= 65535 && num_q_heads <= 65535 && q_len < (1LL << 31) && kv_len < (1LL << 31),
                MOJO_B200_EUNSUPPORTED, "sdpa: shape too large");
+
+  {  // tcgen05/TMEM kernel when the shape is covered
+    AttnSm100Args a;
+    memset(&a, 0, sizeof(a));
+    a.q = query; a.out = out; a.q_rows = q_len; a.q_sb = q_stride_b; a.q_st = q_stride_s; a.q_sh = q_stride_h;
+    a.o_sb = o_stride_b; a.o_st = o_stride_s; a.o_sh = o_stride_h;
+    a.k = key; a.v = value; a.k_b = k_stride_b; a.k_h = k_stride_h; a.k_t = k_stride_s;
+    a.v_b = v_stride_b; a.v_h = v_stride_h; a.v_t = v_stride_s;
+    a.rows_per_block = kv_len; a.num_blocks = batch;
+    a.batch = batch; a.num_q_heads = num_q_heads; a.num_kv_heads = num_kv_heads; a.head_dim = head_dim;
+    a.max_q_len = q_len; a.q_len_dense = q_len; a.kv_len_dense = kv_len; a.softmax_scale = softmax_scale;
+    a.interleave = 0; a.causal = 0; a.dense = 1; a.round_scores = 0; a.dtype = dtype;
+    const int rc = launch_attn_sm100(a, (cudaStream_t)stream);
+    if (rc != kAttnNotEligible) return rc;
+  }
 
   AttnParams p;
   memset(&p, 0, sizeof(p));

@@ -1,0 +1,467 @@
+// MojoPagedPrefillGQA / MojoSdpa on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, fed by
+// TMA.  head_dim 128, bf16/fp16, paged (power-of-two pages >= 8) or dense strided K/V.
+//
+// One CTA per SM (384 threads) owns TWO 128-row query tiles of one (sequence, query head) and walks the KV
+// sequence in 128-key tiles; the two tiles ping-pong so that the tensor pipe works on one while the other is
+// in its softmax:
+//
+//   warp  8      TMA producer: Q tiles once, then K(0) V(0) K(1) V(1) ... through a ring of 32 KB stages
+//                (full/empty mbarriers).  A paged tile is gathered page by page through the block table, one
+//                cp.async.bulk.tensor per (page, 64-column half), landing in the 128B-swizzled K-major layout
+//                UMMA reads ([half][key][128 B]).
+//   warp  9      MMA issuer (one thread): S_t = Q_t K^T   (SS, M128 N128 K16 x 8,  K-major A and B)
+//                                         O_t += P_t V    (TS, A = P from TMEM, B = V as an MN-major operand)
+//                issue order  PV_0(j) QK_0(j+1) PV_1(j) QK_1(j+1): tcgen05 executes in order, so a commit after
+//                QK_t(j+1) also certifies PV_t(j) - which is what lets the softmax warps rescale O in place.
+//   warps 0-3    softmax of tile 0, warps 4-7 softmax of tile 1: thread = query row = TMEM lane.  S row from
+//                TMEM (tcgen05.ld) -> [round to the input dtype, as the golden's einsum] -> * scale, mask ->
+//                running max with LAZY rescaling (O and l are only rescaled when the max grows by more than
+//                2^8, so almost every tile skips the O read-modify-write) -> exp2 -> P (input dtype) written
+//                over S in TMEM (tcgen05.st) -> arrive.  Epilogue: O row / l -> out.
+//   warp 10      TMEM allocation (all 512 columns: S0 S1 O0 O1, P_t aliases the first 64 columns of S_t).
+//
+// FLOPs = 4 * D * (unmasked (q, k) pairs) per query head; the roofline is the bf16 tensor peak.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+#include "attention_sm100.cuh"
+#include "tcgen05.cuh"
+
+namespace mojo {
+
+namespace sm100 {
+
+constexpr int kThreads = 384;
+constexpr int kBM = 128;                      // rows per query tile (two tiles per CTA)
+constexpr int kBN = 128;                      // keys per KV tile
+constexpr int kD = 128;
+constexpr int kHalfBytes = 128 * 128;         // 128 lines of 128 B: one 64-column half of a tile
+constexpr int kTileBytes = 2 * kHalfBytes;    // 32 KB
+constexpr int kStages = 4;                    // K/V ring
+constexpr int kTmemCols = 512;
+constexpr int kLoadWarp = 8, kMmaWarp = 9, kAllocWarp = 10;
+constexpr float kRescaleThreshold = 8.f;      // log2 units
+constexpr size_t kSmemBytes = 1024 + (2 + kStages) * (size_t)kTileBytes + 256;
+
+struct Params {
+  void* out;
+  const int32_t* cu_q;
+  const int32_t* cu_kv;
+  const int32_t* tables;
+  int64_t table_stride;
+  int64_t o_sb, o_st, o_sh;
+  int max_blocks, block_size, log2_bs, box_rows;
+  int num_kv_heads, group, interleave, dense;
+  int q_len_dense, kv_len_dense;
+  float scale_log2;
+};
+
+__device__ __forceinline__ uint32_t ring_stage(uint32_t c) { return c % kStages; }
+__device__ __forceinline__ uint32_t ring_parity(uint32_t c) { return (c / kStages) & 1u; }
+
+template <typename T, bool CAUSAL, bool ROUND_S>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map,
+                      const __grid_constant__ CUtensorMap v_map, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * kTileBytes);
+  uint64_t* q_full = bars;                  // [2]
+  uint64_t* kv_full = bars + 2;             // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;   // [kStages]
+  uint64_t* s_full = kv_empty + kStages;    // [2]  MMA -> softmax: S_t ready
+  uint64_t* p_full = s_full + 2;            // [2]  softmax -> MMA: P_t written (and S_t consumed)
+  uint64_t* o_full = p_full + 2;            // [2]  MMA -> softmax: last PV_t done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, hq = blockIdx.y;
+  const int m_blk = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // causal: longest rows first
+
+  int64_t q_start;
+  int q_len, kv_len;
+  if (p.dense) {
+    q_start = 0;
+    q_len = p.q_len_dense;
+    kv_len = p.kv_len_dense;
+  } else {
+    q_start = p.cu_q[b];
+    q_len = p.cu_q[b + 1] - (int)q_start;
+    kv_len = p.cu_kv ? p.cu_kv[b + 1] - p.cu_kv[b] : q_len;
+  }
+  const int m0 = m_blk * 2 * kBM;
+  if (m0 >= q_len || kv_len <= 0) return;
+  const int off = kv_len - q_len;  // query row t sees keys 0 .. off + t
+  int n_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int first = m0 + t * kBM;
+    int n = 0;
+    if (first < q_len) {
+      const int last = min(first + kBM, q_len) - 1;
+      const int n_end = CAUSAL ? min(kv_len, off + last + 1) : kv_len;
+      n = n_end > 0 ? (n_end + kBN - 1) / kBN : 0;
+    }
+    n_t[t] = n;
+  }
+  const int n_max = max(n_t[0], n_t[1]);
+  if (n_max == 0) return;  // rows that see no key keep the zeros the output was initialised with
+  const int kvh = p.interleave ? hq % p.num_kv_heads : hq / p.group;
+
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);  // one arrive per softmax warp
+      mbar_init(&o_full[t], 1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kAllocWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp >= 8) {
+    reg_dealloc<72>();
+    if (warp == kLoadWarp) {
+      // ---------------------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        tma_prefetch_desc(&q_map);
+        tma_prefetch_desc(&k_map);
+        tma_prefetch_desc(&v_map);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (n_t[t] > 0) {
+            const int row0 = (int)q_start + m0 + t * kBM;
+            mbar_expect_tx(&q_full[t], kTileBytes);
+            tma_load_5d(sQ + t * kTileBytes, &q_map, &q_full[t], 0, row0, 0, hq, p.dense ? b : 0);
+            tma_load_5d(sQ + t * kTileBytes + kHalfBytes, &q_map, &q_full[t], 0, row0, 1, hq, p.dense ? b : 0);
+          }
+        }
+      }
+      const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
+      const int box_rows = p.box_rows;
+      const int boxes_per_tile = kBN / box_rows;
+      const uint32_t box_bytes = (uint32_t)box_rows * 128u;  // one half of one box
+      uint32_t c = 0;
+      for (int j = 0; j < n_max; ++j) {
+        const int tok0 = j * kBN;
+        const int want = p.dense ? 1 : min(boxes_per_tile, (kv_len - tok0 + box_rows - 1) / box_rows);
+#pragma unroll 1
+        for (int is_v = 0; is_v < 2; ++is_v, ++c) {
+          const uint32_t stage = ring_stage(c);
+          uint8_t* dst = sKV + stage * kTileBytes;
+          if (lane == 0) {
+            mbar_wait_bounded(&kv_empty[stage], ring_parity(c) ^ 1u);
+            mbar_expect_tx(&kv_full[stage], 2u * box_bytes * (uint32_t)want);
+          }
+          __syncwarp();
+          const CUtensorMap* map = is_v ? &v_map : &k_map;
+          for (int idx = lane; idx < 2 * want; idx += 32) {
+            const int box = idx >> 1, half = idx & 1;
+            int blk, row;
+            if (p.dense) {
+              blk = b;
+              row = tok0;
+            } else {
+              const int tok = tok0 + box * box_rows;
+              const int page = tok >> p.log2_bs;
+              row = tok & (p.block_size - 1);
+              blk = page < p.max_blocks ? table[page] : -1;  // out-of-range ids are zero-filled by the TMA unit
+            }
+            tma_load_5d(dst + half * kHalfBytes + box * box_bytes, map, &kv_full[stage], 0, row, half, kvh, blk);
+          }
+        }
+      }
+    } else if (warp == kMmaWarp && lane == 0) {
+      // ---------------------------------------------------------------------------- MMA issuer
+      constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kFmt, kBM, kBN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kFmt, kBM, kD, 0, 1);
+      const uint32_t sQ_a = smem_u32(sQ), sKV_a = smem_u32(sKV);
+      auto qk = [&](int t, uint32_t k_stage) {  // S_t = Q_t K^T
+        const uint32_t qa = sQ_a + t * kTileBytes, ka = sKV_a + k_stage * kTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ++ks) {
+          const uint32_t o = (uint32_t)(ks >> 2) * kHalfBytes + (uint32_t)(ks & 3) * 32u;
+          umma_ss(tmem + t * kBN, umma_desc_sw128(qa + o, 16, 1024), umma_desc_sw128(ka + o, 16, 1024), idesc_qk,
+                  ks > 0);
+        }
+      };
+      auto pv = [&](int t, uint32_t v_stage, bool acc) {  // O_t (+)= P_t V
+        const uint32_t va = sKV_a + v_stage * kTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBN / 16; ++ks)
+          umma_ts(tmem + 2 * kBN + t * kD, tmem + t * kBN + ks * 8, umma_desc_sw128(va + ks * 2048u, kHalfBytes, 1024),
+                  idesc_pv, acc || ks > 0);
+      };
+      uint32_t c = 0;
+      mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));  // K(0)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (n_t[t] > 0) {
+          mbar_wait_bounded(&q_full[t], 0);
+          tc_fence_after();
+          qk(t, ring_stage(c));
+          umma_commit(&s_full[t]);
+        }
+      }
+      umma_commit(&kv_empty[ring_stage(c)]);
+      ++c;
+      for (int j = 0; j < n_max; ++j, c += 2) {
+        const uint32_t cv = c, ck = c + 1;
+        const bool more = j + 1 < n_max;
+        mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));  // V(j)
+        if (j < n_t[0]) {
+          mbar_wait_bounded(&p_full[0], (uint32_t)j & 1u);
+          tc_fence_after();
+          pv(0, ring_stage(cv), j > 0);
+          if (j == n_t[0] - 1) umma_commit(&o_full[0]);
+        }
+        if (more) {
+          mbar_wait_bounded(&kv_full[ring_stage(ck)], ring_parity(ck));  // K(j+1)
+          tc_fence_after();
+        }
+        if (j + 1 < n_t[0]) {
+          qk(0, ring_stage(ck));
+          umma_commit(&s_full[0]);
+        }
+        if (j < n_t[1]) {
+          mbar_wait_bounded(&p_full[1], (uint32_t)j & 1u);
+          tc_fence_after();
+          pv(1, ring_stage(cv), j > 0);
+          if (j == n_t[1] - 1) umma_commit(&o_full[1]);
+        }
+        umma_commit(&kv_empty[ring_stage(cv)]);
+        if (j + 1 < n_t[1]) {
+          qk(1, ring_stage(ck));
+          umma_commit(&s_full[1]);
+        }
+        if (more) umma_commit(&kv_empty[ring_stage(ck)]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------------------------------------------------------- softmax warpgroups
+    reg_alloc<216>();
+    const int t = warp >> 2;                       // query tile
+    const int row_local = (warp & 3) * 32 + lane;  // TMEM lane = row of the tile
+    const int n_tiles = n_t[t];
+    if (n_tiles > 0) {
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tS = tmem + lane_base + (uint32_t)(t * kBN);
+      const uint32_t tO = tmem + lane_base + (uint32_t)(2 * kBN + t * kD);
+      const int first_row = m0 + t * kBM;
+      const int row = first_row + row_local;  // row inside the sequence
+      const int limit = CAUSAL ? min(kv_len - 1, off + row) : kv_len - 1;      // last key this row sees
+      const int tile_min_limit = CAUSAL ? min(kv_len - 1, off + first_row) : kv_len - 1;
+      const float scale_log2 = p.scale_log2;
+      float m_ref = -INFINITY, l = 0.f;
+
+      for (int j = 0; j < n_tiles; ++j) {
+        const int n0 = j * kBN;
+        mbar_wait_bounded(&s_full[t], (uint32_t)j & 1u);
+        tc_fence_after();
+        uint32_t sr[kBN];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, sr + q4 * 32);
+        tmem_wait_ld();
+
+        if (ROUND_S) {
+#pragma unroll
+          for (int c = 0; c < kBN; ++c) sr[c] = __float_as_uint(round_through<T>(__uint_as_float(sr[c])));
+        }
+        if (n0 + kBN - 1 > tile_min_limit) {  // diagonal or tail tile (uniform over the warpgroup)
+#pragma unroll
+          for (int c = 0; c < kBN; ++c)
+            if (n0 + c > limit) sr[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kBN; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+        }
+        const float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;  // scale > 0
+
+        if (j == 0) {
+          m_ref = mt;
+        } else {
+          const bool grow = mt > m_ref + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, grow)) {
+            // PV_t(j-1) has completed (it was issued before the QK whose commit we just observed): O is stable
+            float alpha = 1.f;
+            if (grow) {
+              alpha = ex2_approx(m_ref - mt);
+              m_ref = mt;
+              l *= alpha;
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint32_t orow[32];
+              tmem_ld_x32(tO + q4 * 32, orow);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * alpha);
+              tmem_st_x32(tO + q4 * 32, orow);
+            }
+          }
+        }
+        const float base = m_ref == -INFINITY ? 0.f : m_ref;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[q4 * 16 + 2 * c]), scale_log2, -base));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[q4 * 16 + 2 * c + 1]), scale_log2, -base));
+            sum0 += p0;
+            sum1 += p1;
+            pk[c] = pack2<T>(p0, p1);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sr[q4 * 8 + c] = pk[c];  // reuse the low registers for the packed row
+        }
+        l += sum0 + sum1;
+        tmem_st_x32(tS, sr);
+        tmem_st_x32(tS + 32, sr + 32);
+
+        const int valid = kv_len - n0;
+        if (valid < kBN) {
+          // tail tile: V rows past the end of the sequence may hold anything (stale page rows, untouched smem);
+          // P is exactly 0 there but 0 * NaN would poison O, so zero them (both warpgroups may, all store 0)
+          const uint32_t cv = 2u * (uint32_t)j + 1u;
+          mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));
+          uint8_t* sv = sKV + ring_stage(cv) * kTileBytes;
+          const int tid = threadIdx.x & 127;
+          for (int idx = tid; idx < (kBN - valid) * 16; idx += 128) {
+            const int r = valid + (idx >> 4), h = (idx >> 3) & 1, ch = idx & 7;
+            *reinterpret_cast<uint4*>(sv + h * kHalfBytes + r * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
+          }
+          fence_async_smem();
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+
+      // ---- epilogue: O / l -> out
+      mbar_wait_bounded(&o_full[t], 0);
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      T* dst = reinterpret_cast<T*>(p.out) + (int64_t)b * p.o_sb + (q_start + row) * p.o_st + (int64_t)hq * p.o_sh;
+      const bool row_ok = row < q_len;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t orow[32];
+        tmem_ld_x32(tO + q4 * 32, orow);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 v;
+            v.x = pack2<T>(__uint_as_float(orow[8 * c + 0]) * inv, __uint_as_float(orow[8 * c + 1]) * inv);
+            v.y = pack2<T>(__uint_as_float(orow[8 * c + 2]) * inv, __uint_as_float(orow[8 * c + 3]) * inv);
+            v.z = pack2<T>(__uint_as_float(orow[8 * c + 4]) * inv, __uint_as_float(orow[8 * c + 5]) * inv);
+            v.w = pack2<T>(__uint_as_float(orow[8 * c + 6]) * inv, __uint_as_float(orow[8 * c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + q4 * 32 + c * 8) = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kAllocWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : fallback;
+}
+
+}  // namespace sm100
+
+int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
+  using namespace sm100;
+  // ---- coverage
+  const char* impl = getenv("MOJO_B200_ATTN_IMPL");  // "mma" forces the general path, "tcgen05" forbids it
+  const bool forced = impl && !strcmp(impl, "tcgen05");
+  if (impl && !strcmp(impl, "mma")) return kAttnNotEligible;
+  bool ok = a.head_dim == kD && (a.dtype == MOJO_B200_BF16 || a.dtype == MOJO_B200_F16) && a.softmax_scale > 0.f;
+  const int64_t strides[] = {a.k_b, a.k_h, a.k_t, a.v_b, a.v_h, a.v_t, a.q_st, a.q_sh, a.o_st, a.o_sh};
+  for (int64_t st : strides) ok = ok && st > 0 && st % 8 == 0;
+  ok = ok && (a.dense ? (a.q_sb % 8 == 0 && a.o_sb % 8 == 0) : true);
+  ok = ok && aligned16(a.q) && aligned16(a.out) && aligned16(a.k) && aligned16(a.v);
+  int box_rows = kBN;
+  if (!a.dense) {
+    const int64_t bs = a.rows_per_block;
+    ok = ok && bs >= 8 && (bs & (bs - 1)) == 0;
+    box_rows = bs < kBN ? (int)bs : kBN;
+  }
+  ok = ok && a.batch <= 65535 && a.num_q_heads <= 65535;
+  // short query chunks leave most of a 256-row CTA idle: the 64-row general kernel is the better fit
+  if (!forced && a.max_q_len < env_int("MOJO_B200_ATTN_TCGEN05_MIN_Q", 192)) ok = false;
+  if (!ok) {
+    MOJO_REQUIRE(!forced, MOJO_B200_EUNSUPPORTED, "attention: MOJO_B200_ATTN_IMPL=tcgen05 but the shape is not covered");
+    return kAttnNotEligible;
+  }
+
+  CUtensorMap q_map, k_map, v_map;
+  const int64_t q_sb = a.dense ? a.q_sb : a.q_rows * a.q_st;  // paged: a single "batch" (any valid stride)
+  int rc = build_tile_map(a.q, a.dtype, a.q_rows, a.num_q_heads, a.dense ? a.batch : 1, q_sb, a.q_sh, a.q_st, kBM, &q_map);
+  if (rc != 0) return forced ? rc : kAttnNotEligible;
+  rc = build_tile_map(a.k, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.k_b, a.k_h, a.k_t, box_rows, &k_map);
+  if (rc != 0) return forced ? rc : kAttnNotEligible;
+  rc = build_tile_map(a.v, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.v_b, a.v_h, a.v_t, box_rows, &v_map);
+  if (rc != 0) return forced ? rc : kAttnNotEligible;
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.out = a.out;
+  p.cu_q = a.cu_q; p.cu_kv = a.cu_kv; p.tables = a.tables; p.table_stride = a.table_stride;
+  p.o_sb = a.dense ? a.o_sb : 0; p.o_st = a.o_st; p.o_sh = a.o_sh;
+  p.max_blocks = a.max_blocks; p.block_size = (int)a.rows_per_block; p.box_rows = box_rows;
+  while (!a.dense && (1 << p.log2_bs) < p.block_size) ++p.log2_bs;
+  p.num_kv_heads = a.num_kv_heads; p.group = a.num_q_heads / a.num_kv_heads; p.interleave = a.interleave;
+  p.dense = a.dense; p.q_len_dense = (int)a.q_len_dense; p.kv_len_dense = (int)a.kv_len_dense;
+  p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+
+  dim3 grid((unsigned)((a.max_q_len + 2 * kBM - 1) / (2 * kBM)), (unsigned)a.num_q_heads, (unsigned)a.batch);
+#define LAUNCH_SM100(TT, CC, RR)                                                                              \
+  do {                                                                                                        \
+    auto kern = attn_fwd_sm100_kernel<TT, CC, RR>;                                                            \
+    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));   \
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(q_map, k_map, v_map, p);                                     \
+  } while (0)
+  const bool bf16 = a.dtype == MOJO_B200_BF16;
+  if (a.causal) {
+    if (a.round_scores) { if (bf16) LAUNCH_SM100(__nv_bfloat16, true, true); else LAUNCH_SM100(__half, true, true); }
+    else                { if (bf16) LAUNCH_SM100(__nv_bfloat16, true, false); else LAUNCH_SM100(__half, true, false); }
+  } else {
+    if (a.round_scores) { if (bf16) LAUNCH_SM100(__nv_bfloat16, false, true); else LAUNCH_SM100(__half, false, true); }
+    else                { if (bf16) LAUNCH_SM100(__nv_bfloat16, false, false); else LAUNCH_SM100(__half, false, false); }
+  }
+#undef LAUNCH_SM100
+  return check_launch("attn_fwd_sm100_kernel");
+}
+
+}  // namespace mojo
