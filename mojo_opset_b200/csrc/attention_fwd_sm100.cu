@@ -61,7 +61,7 @@ struct Params {
 __device__ __forceinline__ uint32_t ring_stage(uint32_t c) { return c % kStages; }
 __device__ __forceinline__ uint32_t ring_parity(uint32_t c) { return (c / kStages) & 1u; }
 
-template <typename T, bool CAUSAL, bool ROUND_S>
+template <typename T, bool CAUSAL, bool ROUND_S, int EMU>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map,
                       const __grid_constant__ CUtensorMap v_map, const Params p) {
@@ -277,9 +277,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, sr + q4 * 32);
         tmem_wait_ld();
 
-        if (ROUND_S) {
+        if (ROUND_S) {  // the golden's einsum materialises the scores in the input dtype
 #pragma unroll
-          for (int c = 0; c < kBN; ++c) sr[c] = __float_as_uint(round_through<T>(__uint_as_float(sr[c])));
+          for (int c = 0; c < kBN; c += 2) {
+            const uint32_t pk2 = pack2<T>(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+            if (std::is_same<T, __nv_bfloat16>::value) {
+              sr[c] = pk2 << 16;
+              sr[c + 1] = pk2 & 0xffff0000u;
+            } else {
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&pk2));
+              sr[c] = __float_as_uint(f2.x);
+              sr[c + 1] = __float_as_uint(f2.y);
+            }
+          }
         }
         if (n0 + kBN - 1 > tile_min_limit) {  // diagonal or tail tile (uniform over the warpgroup)
 #pragma unroll
@@ -320,21 +330,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           }
         }
         const float base = m_ref == -INFINITY ? 0.f : m_ref;
-        float sum0 = 0.f, sum1 = 0.f;
+        const float2 scale2 = make_float2(scale_log2, scale_log2), nbase2 = make_float2(-base, -base);
+        float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[q4 * 16 + 2 * c]), scale_log2, -base));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[q4 * 16 + 2 * c + 1]), scale_log2, -base));
-            sum0 += p0;
-            sum1 += p1;
-            pk[c] = pack2<T>(p0, p1);
+        for (int c = 0; c < kBN / 2; ++c) {  // pair c = keys 2c, 2c+1 -> one packed P word
+          float2 x = fma2(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), scale2, nbase2);
+          float2 e;
+          if ((c & 3) < EMU) {  // this share of the exponentials runs on the FMA pipe instead of the MUFU
+            e = ex2_emulated2(x);
+          } else {
+            e.x = ex2_approx(x.x);
+            e.y = ex2_approx(x.y);
           }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) sr[q4 * 8 + c] = pk[c];  // reuse the low registers for the packed row
+          if (c & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
+          sr[c] = pack2<T>(e.x, e.y);  // the packed row reuses the low registers (index c <= 2c)
         }
+        const float sum0 = sum_a.x + sum_a.y, sum1 = sum_b.x + sum_b.y;
         l += sum0 + sum1;
         tmem_st_x32(tS, sr);
         tmem_st_x32(tS + 32, sr + 32);
@@ -446,20 +457,27 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
 
   dim3 grid((unsigned)((a.max_q_len + 2 * kBM - 1) / (2 * kBM)), (unsigned)a.num_q_heads, (unsigned)a.batch);
-#define LAUNCH_SM100(TT, CC, RR)                                                                              \
+#define LAUNCH_SM100(TT, PP, EE)                                                                              \
   do {                                                                                                        \
-    auto kern = attn_fwd_sm100_kernel<TT, CC, RR>;                                                            \
+    auto kern = attn_fwd_sm100_kernel<TT, PP, PP, EE>;                                                        \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));   \
     kern<<<grid, kThreads, kSmemBytes, stream>>>(q_map, k_map, v_map, p);                                     \
   } while (0)
+#define LAUNCH_SM100_EMU(TT, PP)                                                \
+  do {                                                                          \
+    if (emu == 0) LAUNCH_SM100(TT, PP, 0);                                      \
+    else if (emu == 1) LAUNCH_SM100(TT, PP, 1);                                 \
+    else LAUNCH_SM100(TT, PP, 2);                                               \
+  } while (0)
+  // the two ops that reach this kernel: paged prefill = causal + scores rounded to the input dtype (golden einsum),
+  // dense SDPA = neither
+  MOJO_REQUIRE((a.causal != 0) == (a.round_scores != 0), MOJO_B200_EUNSUPPORTED,
+               "attention: causal/round_scores combination not built");
+  const int emu = env_int("MOJO_B200_ATTN_EMU", 1);  // quarter-shares of exp2 emulated on the FMA pipe (0..2)
   const bool bf16 = a.dtype == MOJO_B200_BF16;
-  if (a.causal) {
-    if (a.round_scores) { if (bf16) LAUNCH_SM100(__nv_bfloat16, true, true); else LAUNCH_SM100(__half, true, true); }
-    else                { if (bf16) LAUNCH_SM100(__nv_bfloat16, true, false); else LAUNCH_SM100(__half, true, false); }
-  } else {
-    if (a.round_scores) { if (bf16) LAUNCH_SM100(__nv_bfloat16, false, true); else LAUNCH_SM100(__half, false, true); }
-    else                { if (bf16) LAUNCH_SM100(__nv_bfloat16, false, false); else LAUNCH_SM100(__half, false, false); }
-  }
+  if (a.causal) { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, true); else LAUNCH_SM100_EMU(__half, true); }
+  else          { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, false); else LAUNCH_SM100_EMU(__half, false); }
+#undef LAUNCH_SM100_EMU
 #undef LAUNCH_SM100
   return check_launch("attn_fwd_sm100_kernel");
 }

@@ -124,6 +124,49 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: one FMA-pipe instruction for two lanes) -----------------------------------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)),
+        "l"(reinterpret_cast<const uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+
+// 2^x for a pair on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (relative error 7.5e-5, far inside bf16/fp16 rounding of P), n added to the exponent field.
+// x is clamped at -125 so the exponent never underflows: masked scores give 2^-125 instead of 0.
+__device__ __forceinline__ float2 ex2_emulated2(float2 x) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = add2(x, make_float2(kMagic, kMagic));
+  const float2 r = add2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = add2(x, make_float2(-r.x, -r.y));
+  float2 q = fma2(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  q = fma2(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = fma2(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 out;
+  out.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23));
+  out.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23));
+  return out;
+}
+
 // two fp32 -> packed 16-bit pair, `lo` in bits [0,16)
 template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {

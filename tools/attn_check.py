@@ -125,7 +125,7 @@ def time_it(fn, iters=10, warmup=3):
     return a.elapsed_time(b) / iters
 
 
-def bench():
+def bench(impls=("mma", "tcgen05")):
     Hq, Hkv, D, bs, T = 32, 8, 128, 16, 8192
     nb = T // bs + 10
     kc = torch.empty(nb, Hkv, bs, D, dtype=torch.bfloat16, device=DEV).normal_()
@@ -134,14 +134,14 @@ def bench():
     table = torch.randperm(nb, device=DEV)[: T // bs].view(1, -1).to(torch.int32)
     cu = torch.tensor([0, T], dtype=torch.int32, device=DEV)
     flops = 4 * Hq * D * (T * (T + 1) // 2)
-    for impl in ("mma", "tcgen05"):
+    for impl in impls:
         set_impl(impl)
         ms = time_it(lambda: F.paged_prefill_gqa(q, kc, vc, cu, table, None, None, "AABB", T, T))
         print(f"cfg3 prefill T=8192 causal [{impl}]: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
     Bd, H, S = 2, 24, 4096
     qs, ks, vs = (torch.empty(Bd, S, H, D, dtype=torch.bfloat16, device=DEV).normal_().transpose(1, 2) for _ in range(3))
     flops = 4 * Bd * H * S * S * D
-    for impl in ("mma", "tcgen05"):
+    for impl in impls:
         set_impl(impl)
         ms = time_it(lambda: F.sdpa(qs, ks, vs))
         print(f"cfg5 sdpa B2 H24 S4096 [{impl}]: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
@@ -152,6 +152,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-bench", action="store_true")
     ap.add_argument("--only", default=None)
+    ap.add_argument("--bench-impl", default=None)
     args = ap.parse_args()
     if args.only in (None, "sdpa"):
         check_sdpa(1, 1, 1, 128, 128)
@@ -170,7 +171,7 @@ def main():
         check_prefill([384, 0, 129], [100, 50, 7], 4, 2, 16, layout="ABAB")
         check_prefill([333], [95], 2, 2, 8, dtype=torch.float16)
     if not args.no_bench:
-        bench()
+        bench((args.bench_impl,) if args.bench_impl else ("mma", "tcgen05"))
 
 
 if __name__ == "__main__":
