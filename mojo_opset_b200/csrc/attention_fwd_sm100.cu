@@ -183,8 +183,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           }
         }
       }
-    } else if (warp == kMmaWarp && lane == 0) {
-      // ---------------------------------------------------------------------------- MMA issuer
+    } else if (warp == kMmaWarp) {
+      // ---------------------------------------------------------------------------- MMA issuer (whole warp, converged)
       constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
       constexpr uint32_t idesc_qk = umma_idesc_f16(kFmt, kBM, kBN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(kFmt, kBM, kD, 0, 1);
