@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         objects.append(obj)
         if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj])
+            jobs.append([nvcc, *NVCC_FLAGS, *os.environ.get("MOJO_B200_EXTRA_NVCC_FLAGS", "").split(), "-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:

@@ -56,7 +56,18 @@ struct Params {
   int num_kv_heads, group, interleave, dense;
   int q_len_dense, kv_len_dense;
   float scale_log2;
+  long long* trace;  // developer timeline (MOJO_ATTN_TRACE builds only, tools/attn_trace.py)
 };
+
+#ifdef MOJO_ATTN_TRACE
+#define TRACE(role, j, ev)                                                                                   \
+  do {                                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (j) < 32)            \
+      p.trace[((role) * 32 + (j)) * 8 + (ev)] = clock64();                                                    \
+  } while (0)
+#else
+#define TRACE(role, j, ev) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t ring_stage(uint32_t c) { return c % kStages; }
 __device__ __forceinline__ uint32_t ring_parity(uint32_t c) { return (c / kStages) & 1u; }
@@ -224,6 +235,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));  // V(j)
         if (j < n_t[0]) {
           mbar_wait_bounded(&p_full[0], (uint32_t)j & 1u);
+          TRACE(2, j, 0);
           tc_fence_after();
           pv(0, ring_stage(cv), j > 0);
           if (j == n_t[0] - 1) umma_commit(&o_full[0]);
@@ -236,8 +248,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           qk(0, ring_stage(ck));
           umma_commit(&s_full[0]);
         }
+        TRACE(2, j, 1);
         if (j < n_t[1]) {
           mbar_wait_bounded(&p_full[1], (uint32_t)j & 1u);
+          TRACE(2, j, 2);
           tc_fence_after();
           pv(1, ring_stage(cv), j > 0);
           if (j == n_t[1] - 1) umma_commit(&o_full[1]);
@@ -248,6 +262,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           umma_commit(&s_full[1]);
         }
         if (more) umma_commit(&kv_empty[ring_stage(ck)]);
+        TRACE(2, j, 3);
       }
     }
     __syncwarp();
@@ -271,11 +286,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       for (int j = 0; j < n_tiles; ++j) {
         const int n0 = j * kBN;
         mbar_wait_bounded(&s_full[t], (uint32_t)j & 1u);
+        if ((warp & 3) == 0) TRACE(t, j, 0);
         tc_fence_after();
         uint32_t sr[kBN];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, sr + q4 * 32);
         tmem_wait_ld();
+        if ((warp & 3) == 0) TRACE(t, j, 1);
 
         if (ROUND_S) {  // the golden's einsum materialises the scores in the input dtype
 #pragma unroll
@@ -329,6 +346,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
             }
           }
         }
+        if ((warp & 3) == 0) TRACE(t, j, 2);
         const float base = m_ref == -INFINITY ? 0.f : m_ref;
         const float2 scale2 = make_float2(scale_log2, scale_log2), nbase2 = make_float2(-base, -base);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
@@ -347,6 +365,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         }
         const float sum0 = sum_a.x + sum_a.y, sum1 = sum_b.x + sum_b.y;
         l += sum0 + sum1;
+        if ((warp & 3) == 0) TRACE(t, j, 3);
         tmem_st_x32(tS, sr);
         tmem_st_x32(tS + 32, sr + 32);
 
@@ -368,6 +387,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if ((warp & 3) == 0) TRACE(t, j, 4);
       }
 
       // ---- epilogue: O / l -> out
@@ -455,6 +475,9 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.num_kv_heads = a.num_kv_heads; p.group = a.num_q_heads / a.num_kv_heads; p.interleave = a.interleave;
   p.dense = a.dense; p.q_len_dense = (int)a.q_len_dense; p.kv_len_dense = (int)a.kv_len_dense;
   p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+#ifdef MOJO_ATTN_TRACE
+  if (const char* tp = getenv("MOJO_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
+#endif
 
   dim3 grid((unsigned)((a.max_q_len + 2 * kBM - 1) / (2 * kBM)), (unsigned)a.num_q_heads, (unsigned)a.batch);
 #define LAUNCH_SM100(TT, PP, EE)                                                                              \
@@ -473,7 +496,8 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   // dense SDPA = neither
   MOJO_REQUIRE((a.causal != 0) == (a.round_scores != 0), MOJO_B200_EUNSUPPORTED,
                "attention: causal/round_scores combination not built");
-  const int emu = env_int("MOJO_B200_ATTN_EMU", 1);  // quarter-shares of exp2 emulated on the FMA pipe (0..2)
+  // quarter-shares of the exponentials emulated on the FMA pipe (0..2); measured best: 1 for SDPA, 0 for prefill
+  const int emu = env_int("MOJO_B200_ATTN_EMU", a.causal ? 0 : 1);
   const bool bf16 = a.dtype == MOJO_B200_BF16;
   if (a.causal) { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, true); else LAUNCH_SM100_EMU(__half, true); }
   else          { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, false); else LAUNCH_SM100_EMU(__half, false); }

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Developer tool: per-iteration timeline of CTA 0 of the tcgen05 attention kernel (needs a build with
+MOJO_B200_EXTRA_NVCC_FLAGS=-DMOJO_ATTN_TRACE)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["MOJO_BACKEND"] = "b200"
+os.environ["MOJO_B200_ATTN_IMPL"] = "tcgen05"
+buf = torch.zeros(3 * 32 * 8, dtype=torch.int64, device="cuda")
+os.environ["MOJO_B200_ATTN_TRACE_PTR"] = str(buf.data_ptr())
+from mojo_opset_b200 import functional as F  # noqa: E402
+
+Bd, H, S, D = 2, 24, 4096, 128
+qs, ks, vs = (torch.empty(Bd, S, H, D, dtype=torch.bfloat16, device="cuda").normal_().transpose(1, 2) for _ in range(3))
+for _ in range(3):
+    F.sdpa(qs, ks, vs)
+torch.cuda.synchronize()
+t = buf.cpu().view(3, 32, 8)
+base = int(t[0, 4, 0])
+names = ["sm0", "sm1", "mma"]
+for j in range(4, 14):
+    for r in range(3):
+        ev = [int(x) - base for x in t[r, j, :5]]
+        print(f"j={j:2d} {names[r]}: " + " ".join(f"{e:7d}" for e in ev))
+print("softmax events: 0 S ready | 1 S in regs | 2 max+rescale done | 3 exp done | 4 arrived")
+print("mma events:     0 P0 ready | 1 PV0+QK0 issued | 2 P1 ready | 3 PV1+QK1 issued")
