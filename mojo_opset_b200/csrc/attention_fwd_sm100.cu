@@ -53,7 +53,8 @@ struct Params {
   int64_t table_stride;
   int64_t o_sb, o_st, o_sh;
   int max_blocks, block_size, log2_bs, box_rows;
-  int num_kv_heads, group, interleave, dense;
+  int num_q_heads, num_kv_heads, group, interleave, dense;
+  int batch, m_blocks;
   int q_len_dense, kv_len_dense;
   float scale_log2;
   long long* trace;  // developer timeline (MOJO_ATTN_TRACE builds only, tools/attn_trace.py)
@@ -62,7 +63,7 @@ struct Params {
 #ifdef MOJO_ATTN_TRACE
 #define TRACE(role, j, ev)                                                                                   \
   do {                                                                                                       \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (j) < 32)            \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (j) < 32)            \
       p.trace[((role) * 32 + (j)) * 8 + (ev)] = clock64();                                                    \
   } while (0)
 #else
@@ -90,8 +91,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, hq = blockIdx.y;
-  const int m_blk = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // causal: longest rows first
+  // 1-D grid in longest-processing-time order: CTAs are scheduled in linear order, so the query blocks with the most
+  // keys (causal: the last ones) of EVERY (head, sequence) go first and the short ones fill the tail; heads vary
+  // fastest so the q heads of one KV group run together and share K/V tiles in L2.
+  const int hq = (int)(blockIdx.x % (unsigned)p.num_q_heads);
+  const int rest = (int)(blockIdx.x / (unsigned)p.num_q_heads);
+  const int b = rest % p.batch;
+  const int m_blk = p.m_blocks - 1 - rest / p.batch;
 
   int64_t q_start;
   int q_len, kv_len;
@@ -448,7 +454,6 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
     ok = ok && bs >= 8 && (bs & (bs - 1)) == 0;
     box_rows = bs < kBN ? (int)bs : kBN;
   }
-  ok = ok && a.batch <= 65535 && a.num_q_heads <= 65535;
   // short query chunks leave most of a 256-row CTA idle: the 64-row general kernel is the better fit
   if (!forced && a.max_q_len < env_int("MOJO_B200_ATTN_TCGEN05_MIN_Q", 192)) ok = false;
   if (!ok) {
@@ -479,7 +484,11 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   if (const char* tp = getenv("MOJO_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
 #endif
 
-  dim3 grid((unsigned)((a.max_q_len + 2 * kBM - 1) / (2 * kBM)), (unsigned)a.num_q_heads, (unsigned)a.batch);
+  p.num_q_heads = a.num_q_heads; p.batch = a.batch;
+  p.m_blocks = (int)((a.max_q_len + 2 * kBM - 1) / (2 * kBM));
+  const int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch;
+  MOJO_REQUIRE(num_ctas <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "attention: grid too large");
+  dim3 grid((unsigned)num_ctas, 1, 1);
 #define LAUNCH_SM100(TT, PP, EE)                                                                              \
   do {                                                                                                        \
     auto kern = attn_fwd_sm100_kernel<TT, PP, PP, EE>;                                                        \
