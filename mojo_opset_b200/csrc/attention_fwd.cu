@@ -374,6 +374,39 @@ static int launch_attn_mma(const KvDesc& kv, AttnParams& p, int head_dim, int dt
   return check_launch("attn_fwd_mma_kernel");
 }
 
+// Output rows no attention CTA writes must read as zeros (golden: `torch.zeros_like(query)`, attention.py:384):
+// tokens past cu_q_lens[batch], every row of a sequence without keys, and - when kv_len < q_len - the leading rows
+// whose causal window is empty.  Usually none exist and every CTA exits at once; the host no longer memsets `out`.
+__global__ void prefill_zero_unseen_rows_kernel(void* out, const int32_t* cu_q, const int32_t* cu_kv, int batch,
+                                                int64_t total_q, int num_q_heads, int head_dim, int64_t o_st,
+                                                int64_t o_sh, int no_kv) {
+  const int b = blockIdx.x;  // b == batch: the tail after the last sequence
+  int64_t r0, r1;
+  if (b == batch) {
+    r0 = cu_q[batch];
+    r1 = total_q;
+  } else {
+    const int64_t q_start = cu_q[b];
+    const int64_t q_len = cu_q[b + 1] - q_start;
+    const int64_t kv_len = no_kv ? 0 : (cu_kv ? (int64_t)cu_kv[b + 1] - cu_kv[b] : q_len);
+    r0 = q_start;
+    r1 = q_start + (kv_len <= 0 ? q_len : min(q_len, max((int64_t)0, q_len - kv_len)));
+  }
+  r0 = max(r0, (int64_t)0);
+  r1 = min(r1, total_q);
+  if (r1 <= r0) return;
+  const int words = head_dim / 2;  // 2-byte elements, rows 4-byte aligned (checked by the launcher)
+  const int64_t per_row = (int64_t)num_q_heads * words;
+  uint16_t* base = reinterpret_cast<uint16_t*>(out);
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < (r1 - r0) * per_row;
+       i += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t r = r0 + i / per_row;
+    const int rem = (int)(i % per_row);
+    const int h = rem / words, w = rem % words;
+    *reinterpret_cast<uint32_t*>(base + r * o_st + (int64_t)h * o_sh + 2 * w) = 0u;
+  }
+}
+
 }  // namespace mojo
 
 extern "C" int mojo_b200_paged_prefill_gqa(
@@ -391,7 +424,7 @@ extern "C" int mojo_b200_paged_prefill_gqa(
                MOJO_B200_EINVAL, "paged_prefill: bad sizes");
   MOJO_REQUIRE(num_q_heads % num_kv_heads == 0, MOJO_B200_EINVAL, "paged_prefill: Hq %d not a multiple of Hkv %d",
                num_q_heads, num_kv_heads);
-  if (total_q_tokens == 0 || batch == 0 || max_blocks_per_seq == 0 || num_blocks == 0) return 0;
+  if (total_q_tokens == 0) return 0;
   MOJO_REQUIRE(query && key_cache && value_cache && cu_q_lens && block_tables && out, MOJO_B200_EINVAL,
                "paged_prefill: null tensor pointer");
   MOJO_REQUIRE(is_causal, MOJO_B200_EUNSUPPORTED, "paged_prefill: only causal attention is built");
@@ -402,6 +435,15 @@ extern "C" int mojo_b200_paged_prefill_gqa(
   MOJO_REQUIRE(block_size >= 8 && (block_size & (block_size - 1)) == 0, MOJO_B200_EUNSUPPORTED,
                "paged_prefill: block_size %d must be a power of two >= 8", block_size);
   MOJO_REQUIRE(batch <= 65535 && num_q_heads <= 65535, MOJO_B200_EUNSUPPORTED, "paged_prefill: grid too large");
+  MOJO_REQUIRE(head_dim % 2 == 0 && ((o_stride_t | o_stride_h) % 2) == 0 && ((uintptr_t)out & 3) == 0,
+               MOJO_B200_EUNSUPPORTED, "paged_prefill: out strides must be even and the base 4-byte aligned");
+  {
+    const int no_kv = max_blocks_per_seq == 0 || num_blocks == 0;
+    prefill_zero_unseen_rows_kernel<<<dim3((unsigned)batch + 1, 8), 256, 0, (cudaStream_t)stream>>>(
+        out, cu_q_lens, cu_total_seq_lens, batch, total_q_tokens, num_q_heads, head_dim, o_stride_t, o_stride_h, no_kv);
+    const int rc = check_launch("prefill_zero_unseen_rows_kernel");
+    if (rc != 0 || batch == 0 || no_kv) return rc;
+  }
   if (max_q_len <= 0 || max_q_len > total_q_tokens) max_q_len = total_q_tokens;
 
   {  // tcgen05/TMEM kernel when the shape is covered

@@ -303,11 +303,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         if (ROUND_S) {  // the golden's einsum materialises the scores in the input dtype
 #pragma unroll
           for (int c = 0; c < kBN; c += 2) {
-            const uint32_t pk2 = pack2<T>(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
             if (std::is_same<T, __nv_bfloat16>::value) {
-              sr[c] = pk2 << 16;
-              sr[c + 1] = pk2 & 0xffff0000u;
+              // packing against a zero low half leaves exactly the fp32 bit pattern of the rounded value:
+              // one F2FP per score, no unpack
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(sr[c]) : "f"(__uint_as_float(sr[c])), "f"(0.f));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(sr[c + 1]) : "f"(__uint_as_float(sr[c + 1])), "f"(0.f));
             } else {
+              const uint32_t pk2 = pack2<T>(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
               const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&pk2));
               sr[c] = __float_as_uint(f2.x);
               sr[c + 1] = __float_as_uint(f2.y);
@@ -489,17 +491,17 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   const int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch;
   MOJO_REQUIRE(num_ctas <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "attention: grid too large");
   dim3 grid((unsigned)num_ctas, 1, 1);
-#define LAUNCH_SM100(TT, PP, EE)                                                                              \
+#define LAUNCH_SM100(TT, PP, RR, EE)                                                                             \
   do {                                                                                                        \
-    auto kern = attn_fwd_sm100_kernel<TT, PP, PP, EE>;                                                        \
+    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, EE>;                                                        \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));   \
     kern<<<grid, kThreads, kSmemBytes, stream>>>(q_map, k_map, v_map, p);                                     \
   } while (0)
 #define LAUNCH_SM100_EMU(TT, PP)                                                \
   do {                                                                          \
-    if (emu == 0) LAUNCH_SM100(TT, PP, 0);                                      \
-    else if (emu == 1) LAUNCH_SM100(TT, PP, 1);                                 \
-    else LAUNCH_SM100(TT, PP, 2);                                               \
+    if (emu == 0) LAUNCH_SM100(TT, PP, PP, 0);                                  \
+    else if (emu == 1) LAUNCH_SM100(TT, PP, PP, 1);                             \
+    else LAUNCH_SM100(TT, PP, PP, 2);                                           \
   } while (0)
   // the two ops that reach this kernel: paged prefill = causal + scores rounded to the input dtype (golden einsum),
   // dense SDPA = neither

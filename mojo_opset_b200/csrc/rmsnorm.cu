@@ -3,9 +3,11 @@
 //   sum = round_T(x + residual)                      (eager add materialises in the input dtype)
 //   y   = round_T(sum * (1 / sqrt(mean(sum^2) + eps)) * w)
 //
-// A row is owned by a group of TPR threads (a warp for head_dim-sized rows such as q/k-norm, a whole CTA
-// for hidden-sized rows).  Each thread keeps its slice of the row in registers between the reduction and
-// the scaling, so x / residual are read exactly once: bytes = (2 reads + 2 writes) * rows * H * sizeof(T) + H.
+// A row is owned by a group of TPR threads - the narrowest power of two that keeps the row register-resident
+// at 4 x 16 B per thread (4 threads for head_dim-sized q/k-norm rows, 128 for hidden 4096) - and a 256-thread
+// CTA carries 256 / TPR rows, so every thread has 4 (8 with a residual) independent 16-byte loads in flight
+// before the reduction.  Each thread keeps its slice of the row in registers between the reduction and the
+// scaling, so x / residual are read exactly once: bytes = (2 reads + 2 writes) * rows * H * sizeof(T) + H.
 #include "common.cuh"
 
 namespace mojo {
@@ -22,13 +24,15 @@ template <typename T, int VEC> __device__ __forceinline__ void st_pack(T* p, con
   *reinterpret_cast<PackN<T, VEC>*>(p) = v;
 }
 
+constexpr int kNormCta = 256;
+
 template <typename T, int VEC, int TPR, bool HAS_RES>
-__global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
+__global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kernel(
     const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, T* __restrict__ y,
     T* __restrict__ sum_out, int64_t rows, int hidden, int64_t x_rs, int64_t res_rs, int64_t y_rs, int64_t sum_rs,
     float eps) {
   constexpr int N = VEC;
-  constexpr int ROWS_PER_CTA = (TPR >= 128 ? 1 : 128 / TPR);
+  constexpr int ROWS_PER_CTA = (TPR >= kNormCta ? 1 : kNormCta / TPR);
   const int lane_in_row = threadIdx.x % TPR;
   const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + threadIdx.x / TPR;
   const bool active = row < rows;
@@ -48,9 +52,8 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
           const PackN<T, VEC> b = ld_pack<T, VEC>(rr + (int64_t)v * N);
 #pragma unroll
           for (int e = 0; e < N; ++e) a.v[e] = DType<T>::from_f(__fadd_rn(DType<T>::to_f(a.v[e]), DType<T>::to_f(b.v[e])));
-          if (sum_out) st_pack<T, VEC>(sum_out + row * sum_rs + (int64_t)v * N, a);
         }
-        keep[i] = a;
+        keep[i] = a;  // the rounded sum is stored together with y: a pure read phase, then a pure write phase
 #pragma unroll
         for (int e = 0; e < N; ++e) {
           const float f = DType<T>::to_f(a.v[e]);
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
     }
   }
 
-  // reduce ss over the TPR threads of the row
+  // reduce ss over the TPR threads of the row (fixed order: deterministic)
   if constexpr (TPR <= 32) {
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -84,13 +87,12 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
     __syncthreads();
-    float t = (threadIdx.x < TPR / 32) ? part[threadIdx.x] : 0.f;
-    if (threadIdx.x < 32) {
-      t = warp_sum(t);
-      if (threadIdx.x == 0) part[0] = t;
-    }
-    __syncthreads();
-    ss = part[0];
+    constexpr int WPR = TPR / 32;  // warps per row
+    const int w0 = (threadIdx.x / TPR) * WPR;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) t += part[w0 + i];
+    ss = t;
   }
   if (!active) return;
 
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(TPR >= 128 ? TPR : 128) rmsnorm_kernel(
       for (int e = 0; e < N; ++e)
         o.v[e] = DType<T>::from_f(__fmul_rn(__fmul_rn(DType<T>::to_f(keep[i].v[e]), inv), DType<T>::to_f(g.v[e])));
       st_pack<T, VEC>(yr + (int64_t)v * N, o);
+      if (HAS_RES && sum_out) st_pack<T, VEC>(sum_out + row * sum_rs + (int64_t)v * N, keep[i]);
     }
   }
   for (int v = lane_in_row + kMaxVecsPerThread * TPR; v < vecs; v += TPR) {
@@ -137,19 +140,32 @@ static int launch_rmsnorm(const void* x, const void* res, const void* w, void* y
   const int vecs = hidden / VEC;
 #define RUN(TPR)                                                                                              \
   do {                                                                                                        \
-    constexpr int RPC = (TPR >= 128 ? 1 : 128 / TPR);                                                         \
+    constexpr int RPC = (TPR >= kNormCta ? 1 : kNormCta / TPR);                                               \
     const int64_t ctas = (rows + RPC - 1) / RPC;                                                              \
-    rmsnorm_kernel<T, VEC, TPR, HAS_RES><<<(unsigned)ctas, (TPR >= 128 ? TPR : 128), 0, s>>>(                 \
+    rmsnorm_kernel<T, VEC, TPR, HAS_RES><<<(unsigned)ctas, (TPR > kNormCta ? TPR : kNormCta), 0, s>>>(        \
         (const T*)x, (const T*)res, (const T*)w, (T*)y, (T*)sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, \
         eps);                                                                                                 \
   } while (0)
-  // pick the narrowest group that keeps the row register-resident (<= 4 packs per thread)
-  if (vecs <= 8) RUN(8);
-  else if (vecs <= 32 * 2) RUN(32);
-  else if (vecs <= 128 * 2) RUN(128);
-  else if (vecs <= 256 * 2) RUN(256);
-  else if (vecs <= 512 * 4) RUN(512);
-  else RUN(1024);
+  // the narrowest group that keeps the row register-resident with FOUR 16-byte loads in flight per thread
+  // (4 packs of x, or 2 of x + 2 of the residual): measured best on B200 - wider groups pay for the CTA-level
+  // reduction, narrower ones lose occupancy to registers (sweep in profiles/README.md)
+  const int packs = HAS_RES ? 2 : kMaxVecsPerThread;
+  int tpr = 4;
+  while (tpr < 1024 && vecs > tpr * packs) tpr *= 2;
+  // ... widened while the grid would leave SMs idle (decode-sized row counts) and a thread still has >= 2 packs
+  auto ctas_for = [&](int t) { return (rows + (t >= kNormCta ? 1 : kNormCta / t) - 1) / (t >= kNormCta ? 1 : kNormCta / t); };
+  while (tpr < 1024 && vecs >= tpr * 2 && ctas_for(tpr) < 2 * kNumSMs) tpr *= 2;
+  switch (tpr) {
+    case 4: RUN(4); break;
+    case 8: RUN(8); break;
+    case 16: RUN(16); break;
+    case 32: RUN(32); break;
+    case 64: RUN(64); break;
+    case 128: RUN(128); break;
+    case 256: RUN(256); break;
+    case 512: RUN(512); break;
+    default: RUN(1024); break;
+  }
 #undef RUN
   return check_launch("rmsnorm_kernel");
 }

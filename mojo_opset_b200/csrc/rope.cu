@@ -81,10 +81,81 @@ __global__ void __launch_bounds__(256) apply_rope_kernel(const RopeArgs a) {
                                 a.k_h, a.ko_h, cos, sin, a.head_dim, a.rope_dim);
 }
 
+
+// Fast path: one CTA per token, a thread owns ONE output slice position of a head - a pass-through slice, a
+// first-half slice (x1*cos1 - x2*sin1) or a second-half slice (x2*cos2 + x1*sin2) - so it needs just one cos
+// and one sin slice (read once per thread, not once per head) and walks the q then k heads in steps of
+// 256 / SLICES.  Kept deliberately lean (<= 40 registers, two 16-byte loads per trip): on B200 a streaming
+// kernel is fastest at FULL occupancy with one vector per thread in flight - unrolling more loads per thread
+// costs registers, hence resident warps, and measured slower (tools/microbench/stream3.cu).  The partner slice
+// is loaded by two threads of the same warp instruction (one L1 request).  No integer division in the loop.
+// Requires SLICES = head_dim / VEC to be a power of two <= 32.
+template <typename T, typename C, int VEC, bool ROUND_T, int SLICES>
+__global__ void __launch_bounds__(256, 6) apply_rope_slice_kernel(const RopeArgs a) {
+  constexpr int HSLOTS = 256 / SLICES;
+  const uint32_t tok = blockIdx.x;
+  const uint32_t b = tok / (uint32_t)a.seq;
+  const uint32_t s = tok - b * (uint32_t)a.seq;
+  const int sl = threadIdx.x % SLICES, hs = threadIdx.x / SLICES;
+  const int nope = a.head_dim - a.rope_dim, half = a.rope_dim / 2;
+  const int off = sl * VEC;  // this thread's output slice inside a head
+  const bool rotary = off >= nope;
+  const bool second = off >= nope + half;
+  const int partner = second ? off - half : off + half;
+  const T* qs = (const T*)a.q + (int64_t)b * a.q_b + (int64_t)s * a.q_s;
+  const T* ks = (const T*)a.k + (int64_t)b * a.k_b + (int64_t)s * a.k_s - (int64_t)a.q_heads * a.k_h;
+  T* qd = (T*)a.qo + (int64_t)b * a.qo_b + (int64_t)s * a.qo_s;
+  T* kd = (T*)a.ko + (int64_t)b * a.ko_b + (int64_t)s * a.ko_s - (int64_t)a.q_heads * a.ko_h;
+  const int total = a.q_heads + a.k_heads;
+  Pack<C, VEC> cs, sn;
+  if (rotary) {
+    const int64_t row = (int64_t)b * a.cos_b + (int64_t)s * a.cos_s + (off - nope);
+    cs = *reinterpret_cast<const Pack<C, VEC>*>((const C*)a.cos + row);
+    sn = *reinterpret_cast<const Pack<C, VEC>*>((const C*)a.sin + row);
+  }
+#pragma unroll 1
+  for (int h = hs; h < total; h += HSLOTS) {
+    const T* src = h < a.q_heads ? qs + (int64_t)h * a.q_h : ks + (int64_t)h * a.k_h;
+    T* dst = h < a.q_heads ? qd + (int64_t)h * a.qo_h : kd + (int64_t)h * a.ko_h;
+    Pack<T, VEC> o = *reinterpret_cast<const Pack<T, VEC>*>(src + off);
+    if (rotary) {
+      const Pack<T, VEC> xb = *reinterpret_cast<const Pack<T, VEC>*>(src + partner);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float x = DType<T>::to_f(o.v[e]), y = DType<T>::to_f(xb.v[e]);
+        // rotate_half(x) = cat(-x2, x1): the partner enters negated in the first half only
+        float p = __fmul_rn(x, DType<C>::to_f(cs.v[e])), q = __fmul_rn(second ? y : -y, DType<C>::to_f(sn.v[e]));
+        if (ROUND_T) {
+          p = round_through<T>(p);
+          q = round_through<T>(q);
+        }
+        o.v[e] = DType<T>::from_f(__fadd_rn(p, q));
+      }
+    }
+    *reinterpret_cast<Pack<T, VEC>*>(dst + off) = o;
+  }
+}
+
+template <typename T, typename C, int VEC, bool ROUND_T>
+static bool launch_rope_fast(const RopeArgs& a, int64_t tokens, cudaStream_t s) {
+  if (a.head_dim % VEC) return false;
+  const unsigned grid = (unsigned)tokens;
+  switch (a.head_dim / VEC) {
+    case 8: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 8><<<grid, 256, 0, s>>>(a); return true;
+    case 16: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 16><<<grid, 256, 0, s>>>(a); return true;
+    case 32: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 32><<<grid, 256, 0, s>>>(a); return true;
+    default: return false;
+  }
+}
+
 template <typename T, typename C, bool ROUND_T>
 static int launch_rope(const RopeArgs& a, int64_t tokens, int vec, cudaStream_t s) {
   const int64_t work = (int64_t)(a.q_heads + a.k_heads) * ((a.head_dim - a.rope_dim / 2) / vec);
   int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
+  // widest vectors and a power-of-two slice count per head (every production shape): slice-per-thread kernel
+  if (vec == 16 / (int)sizeof(T) && work >= 192) {
+    if (launch_rope_fast<T, C, 16 / (int)sizeof(T), ROUND_T>(a, tokens, s)) return check_launch("apply_rope_slice_kernel");
+  }
   switch (vec) {
     case 8: apply_rope_kernel<T, C, (sizeof(T) == 2 ? 8 : 4), ROUND_T><<<(unsigned)tokens, threads, 0, s>>>(a); break;
     case 4: apply_rope_kernel<T, C, 4, ROUND_T><<<(unsigned)tokens, threads, 0, s>>>(a); break;

@@ -370,9 +370,10 @@ def paged_prefill_gqa(
     tables = block_tables if block_tables.stride(-1) == 1 or block_tables.shape[1] <= 1 else block_tables.contiguous()
     cu_q = cu_q_lens.contiguous()
     cu_kv = None if cu_total_seq_lens is None else cu_total_seq_lens.contiguous()
-    # rows of empty sequences (and tokens past cu_q_lens[-1]) stay zero, as in the golden
-    out = torch.zeros((total_q, num_q_heads, head_dim), dtype=query.dtype, device=dev)
-    if total_q == 0 or batch == 0:
+    # rows no query block covers (tokens past cu_q_lens[-1], sequences without keys) are zero-filled by the
+    # library itself, as in the golden: no host-side memset of the whole output
+    out = torch.empty((total_q, num_q_heads, head_dim), dtype=query.dtype, device=dev)
+    if total_q == 0:
         return out
     max_blocks = tables.shape[1]
     q_hint = total_q if max_q_len is None else min(int(max_q_len), total_q)
