@@ -193,6 +193,34 @@ MOJO_B200_API int mojo_b200_sdpa(const void* query, const void* key, const void*
                    int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
                    float softmax_scale, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * MojoGemmAllReduce.forward           mojo_opset/core/operators/compute_with_comm.py:57-117
+ *                                     (fused precedent: backends/ttx/operators/compute_with_comm.py:102-167)
+ *
+ * out[m, n] = all_reduce_sum over `world` ranks of ( x[m, k] @ weight[n, k]^T + bias[n] )   (bias on every rank,
+ * as the reference adds it before the all-reduce).  ONE persistent kernel: tcgen05 GEMM, partial tiles pushed
+ * over NVLink into the tile owner's workspace, fp32 reduction in rank order (bit-identical on all ranks),
+ * reduced tiles broadcast to every rank.  world == 1 is a plain GEMM (no workspace).
+ *
+ * The workspace is "symmetric": every rank allocates the same number of bytes with mojo_b200_symm_alloc
+ * (cudaMalloc, zero-filled), exports it (64-byte CUDA IPC handle), exchanges handles out of band (the host side
+ * uses torch.distributed) and opens its peers' handles; peer_workspaces[r] is rank r's workspace as mapped in
+ * THIS process (peer_workspaces[rank] = the local allocation).  The call counter that versions the flags lives in
+ * the workspace itself (device memory), so the launch is CUDA-graph replayable; all ranks must make the same
+ * sequence of calls with the same m.  world must be 1, 2, 4 or 8.  x / weight rows must be 16-byte aligned; dtype bf16 / fp16.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_symm_alloc(size_t bytes, void** ptr);
+MOJO_B200_API int mojo_b200_symm_free(void* ptr);
+MOJO_B200_API int mojo_b200_symm_export(void* ptr, void* handle64);
+MOJO_B200_API int mojo_b200_symm_open(const void* handle64, void** peer_ptr);
+MOJO_B200_API int mojo_b200_symm_close(void* peer_ptr);
+MOJO_B200_API size_t mojo_b200_gemm_allreduce_workspace_bytes(int64_t max_m, int64_t n, int world);
+MOJO_B200_API int mojo_b200_gemm_allreduce(
+    const void* x, const void* weight, const void* bias, void* out, int64_t m, int64_t n, int64_t k,
+    int64_t x_row_stride, int64_t w_row_stride, int64_t out_row_stride,
+    void* const* peer_workspaces, size_t workspace_bytes, int64_t workspace_max_m,
+    int world, int rank, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

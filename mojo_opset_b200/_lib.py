@@ -45,6 +45,13 @@ SIGNATURES = {
     "mojo_b200_paged_prefill_gqa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10
                                     + [F, I, I, I, P]),
     "mojo_b200_sdpa": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, I, P]),
+    "mojo_b200_symm_alloc": (I, [Z, ctypes.POINTER(c_void_p)]),
+    "mojo_b200_symm_free": (I, [P]),
+    "mojo_b200_symm_export": (I, [P, P]),
+    "mojo_b200_symm_open": (I, [P, ctypes.POINTER(c_void_p)]),
+    "mojo_b200_symm_close": (I, [P]),
+    "mojo_b200_gemm_allreduce_workspace_bytes": (Z, [L, L, I]),
+    "mojo_b200_gemm_allreduce": (I, [P, P, P, P, L, L, L, L, L, L, ctypes.POINTER(c_void_p), Z, L, I, I, I, P]),
 }
 
 _lock = threading.Lock()

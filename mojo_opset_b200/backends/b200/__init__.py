@@ -5,6 +5,7 @@ from .operators.activation import B200SwiGLU
 from .operators.attention import B200PagedDecodeGQA
 from .operators.attention import B200PagedPrefillGQA
 from .operators.attention import B200Sdpa
+from .operators.compute_with_comm import B200GemmAllReduce
 from .operators.kv_cache import B200StorePagedKVCache
 from .operators.normalization import B200ResidualAddRMSNorm
 from .operators.normalization import B200RMSNorm
@@ -17,6 +18,7 @@ __all__ = [
     "B200PagedDecodeGQA",
     "B200PagedPrefillGQA",
     "B200Sdpa",
+    "B200GemmAllReduce",
     "B200StorePagedKVCache",
     "B200ResidualAddRMSNorm",
     "B200RMSNorm",

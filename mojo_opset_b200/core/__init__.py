@@ -8,6 +8,7 @@ from .operators.activation import MojoSwiGLU
 from .operators.attention import MojoPagedDecodeGQA
 from .operators.attention import MojoPagedPrefillGQA
 from .operators.attention import MojoSdpa
+from .operators.compute_with_comm import MojoGemmAllReduce
 from .operators.kv_cache import MojoStorePagedKVCache
 from .operators.kv_cache import build_paged_kv_chunk_metadata
 from .operators.normalization import MojoResidualAddRMSNorm
@@ -23,6 +24,7 @@ __all__ = [
     "MojoPagedDecodeGQA",
     "MojoPagedPrefillGQA",
     "MojoSdpa",
+    "MojoGemmAllReduce",
     "MojoStorePagedKVCache",
     "build_paged_kv_chunk_metadata",
     "MojoResidualAddRMSNorm",

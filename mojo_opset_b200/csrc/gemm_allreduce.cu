@@ -1,0 +1,607 @@
+// MojoGemmAllReduce (row-parallel o_proj: out = all_reduce(x @ W^T + bias)) as ONE persistent kernel: a tcgen05
+// GEMM whose epilogue pushes each partial tile over NVLink into the tile owner's memory, a reduce step the owner
+// runs as soon as a tile's partials have landed, and a broadcast of the reduced tile into every rank's memory.
+// Reference semantics: mojo_opset/core/operators/compute_with_comm.py:57-117 (F.linear then all_reduce(sum)).
+//
+// Roles of a CTA (192 threads, one CTA per SM, persistent over tiles t = blockIdx.x, +gridDim.x, ...):
+//   warp 0     TMA producer: A [128 x 64] and B [128 x 64] slabs (K-major, 128B swizzle) through a 5-stage ring
+//   warp 1     MMA issuer: tcgen05.mma M128 N128 K16, fp32 accumulators in TMEM, two accumulator buffers so the
+//              epilogue of tile i overlaps the main loop of tile i+1; TMEM allocation
+//   warps 2-5  epilogue: TMEM -> (+bias) -> bf16 -> swizzled 32 KB tile image in shared memory, then
+//                world == 1: image -> out (coalesced);
+//                world  > 1: ONE cp.async.bulk of the image into the owner's partial slot [tile][src rank] in
+//                            PEER memory (NVLink), system fence, epoch flag at the owner.
+//              after the CTA's last GEMM tile the same warps run (two-shot all-reduce, every CTA takes part):
+//                reduce units (owned tile, row slab): wait for the `world` partial flags, bulk-load the slabs into
+//                  shared memory, sum them in fp32 in rank order (deterministic, bit-identical on every rank),
+//                  bulk-store the bf16 slab into the result image of EVERY rank, flag each rank;
+//                copy units (tile): wait for the `world` slab flags, bulk-load the result image, un-swizzle it
+//                  into `out` (coalesced).
+//
+// No wait ever blocks a GEMM tile (all of a CTA's tiles are computed and pushed before its first wait), so the
+// protocol cannot deadlock however the ranks' CTAs are scheduled; every wait is time-bounded (trap after 5 s
+// instead of a hung GPU).  Flags carry the call's epoch and the buffers alternate with its parity, so nothing
+// is ever reset: rank A can only start call n+2 after every rank finished the reduce step of call n+1, hence
+// after every rank's kernel of call n - the last reader of the parity it is about to overwrite - has completed.
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+#include "tcgen05.cuh"
+
+namespace mojo {
+namespace gar {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;
+constexpr int kStages = 5;
+constexpr int kSlabBytes = kBM * kBK * 2;     // 16 KB: one operand slab of one stage
+constexpr int kStageBytes = 2 * kSlabBytes;   // A + B
+constexpr int kImageBytes = kBM * kBN * 2;    // 32 KB: one output tile, 16-bit elements
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxWorld = 8;
+constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kImageBytes + 256;
+constexpr unsigned long long kWaitTimeoutNs = 5000000000ull;
+constexpr size_t kHeaderBytes = 256;
+constexpr int kOneShotMaxTiles = 128;                       // one-shot mode: every rank holds every rank's tile
+constexpr size_t kOneShotMaxPeerBytes = 6u << 20;           // ... so it is used while (world-1) * m * n * 2 B is small
+
+struct Params {
+  void* out;
+  const void* bias;
+  int64_t m, n, k, out_rs;
+  int tiles_m, tiles_n, n_tiles;
+  int world, rank;
+  int owned_cap;    // partial slots per parity = ceil(max tiles / world)
+  int tiles_cap;    // result images per parity = max tiles
+  uint8_t* ws[kMaxWorld];  // workspace base of every rank as mapped HERE (ws[rank] is local memory)
+  size_t off_partial, off_result, off_flag_partial, off_flag_result;
+  int one_shot, one_cap;  // one-shot mode: slots [parity][tile < one_cap][src], flags alike
+  size_t off_one, off_flag_one;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  size_t off_partial, off_result, off_flag_partial, off_flag_result, off_one, off_flag_one, total;
+  int owned_cap, tiles_cap, one_cap;
+};
+
+inline Layout make_layout(int64_t max_m, int64_t n, int world) {
+  Layout l;
+  const int64_t tiles = ((max_m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
+  l.tiles_cap = (int)tiles;
+  l.owned_cap = (int)((tiles + world - 1) / world);
+  l.off_partial = kHeaderBytes;  // [0] epoch counter, [4] finished-CTA counter
+  l.off_result = l.off_partial + (size_t)2 * l.owned_cap * world * kImageBytes;
+  l.off_flag_partial = l.off_result + (size_t)2 * l.tiles_cap * kImageBytes;
+  l.off_flag_result = align_up(l.off_flag_partial + (size_t)2 * l.owned_cap * world * 4, 256);
+  l.one_cap = l.tiles_cap < kOneShotMaxTiles ? l.tiles_cap : kOneShotMaxTiles;
+  l.off_flag_one = align_up(l.off_flag_result + (size_t)2 * l.tiles_cap * world * 4, 256);
+  l.off_one = align_up(l.off_flag_one + (size_t)2 * l.one_cap * world * 4, 1024);
+  l.total = align_up(l.off_one + (size_t)2 * l.one_cap * world * kImageBytes, 256);
+  return l;
+}
+
+__device__ __forceinline__ size_t partial_off(const Params& p, uint32_t par, int local_tile, int src) {
+  return p.off_partial + (((size_t)par * p.owned_cap + local_tile) * p.world + src) * kImageBytes;
+}
+__device__ __forceinline__ size_t result_off(const Params& p, uint32_t par, int tile) {
+  return p.off_result + ((size_t)par * p.tiles_cap + tile) * kImageBytes;
+}
+__device__ __forceinline__ size_t flag_partial_off(const Params& p, uint32_t par, int local_tile, int src) {
+  return p.off_flag_partial + (((size_t)par * p.owned_cap + local_tile) * p.world + src) * 4;
+}
+__device__ __forceinline__ size_t flag_result_off(const Params& p, uint32_t par, int tile, int slab) {
+  return p.off_flag_result + (((size_t)par * p.tiles_cap + tile) * p.world + slab) * 4;
+}
+
+__device__ __forceinline__ size_t one_off(const Params& p, uint32_t par, int tile, int src) {
+  return p.off_one + (((size_t)par * p.one_cap + tile) * p.world + src) * kImageBytes;
+}
+__device__ __forceinline__ size_t flag_one_off(const Params& p, uint32_t par, int tile, int src) {
+  return p.off_flag_one + (((size_t)par * p.one_cap + tile) * p.world + src) * 4;
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// shared -> global (local or peer) bulk copy, tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+// global (local memory, possibly written by peers) -> shared bulk copy completing on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// order this thread's (acquired) view of global memory before its async-proxy reads of it
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void st_flag_sys(uint32_t* flag, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* flag) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
+  if (ld_flag_sys(flag) == epoch) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_flag_sys(flag) != epoch) {
+    __nanosleep(40);
+    if (global_ns() - t0 > kWaitTimeoutNs) __trap();  // a peer never arrived: launch failure, not a hung GPU
+  }
+}
+// L2-coherent 16-byte load (peers wrote this memory: never take a stale L1 line)
+__device__ __forceinline__ uint4 ld_cg(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// byte offset of 16-byte chunk `c` (8 elements) of row `r` inside a tile image: rows of 256 B, chunk index XOR-ed
+// with the row so that the per-row epilogue stores are bank-conflict free
+__device__ __forceinline__ uint32_t image_off(uint32_t r, uint32_t c) { return r * 256u + ((c ^ (r & 7u)) << 4); }
+
+template <typename T> __device__ __forceinline__ void acc2(float (&a)[8], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (std::is_same<T, __nv_bfloat16>::value) {
+      a[2 * i] += __uint_as_float(w[i] << 16);
+      a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    } else {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      a[2 * i] += f.x;
+      a[2 * i + 1] += f.y;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                      const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = smem;
+  uint8_t* image = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(image + kImageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* acc_full = empty + kStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint64_t* aux_bar = acc_empty + 2;        // bulk loads of the reduce / copy phases
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
+  uint32_t* epoch_slot = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+    }
+    mbar_init(aux_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  // The call's epoch lives in DEVICE memory (the workspace header), so a CUDA graph can replay the launch: every
+  // CTA reads the counter at its start, the last CTA to finish publishes the new value.  A CTA can only finish
+  // after every CTA of the grid has started (the finished-CTA count reaches gridDim.x), so all of them read the
+  // same value.  1 .. 0xFFFFFFFE, never 0 (the flags' initial value), parity alternates across the wrap.
+  if (threadIdx.x == 64)
+    *epoch_slot = p.world > 1 ? *reinterpret_cast<volatile uint32_t*>(p.ws[p.rank]) % 0xFFFFFFFEu + 1u : 1u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const int k_blocks = (int)((p.k + kBK - 1) / kBK);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&a_map);
+      tma_prefetch_desc(&b_map);
+      uint32_t c = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+        for (int kb = 0; kb < k_blocks; ++kb, ++c) {
+          const uint32_t s = c % kStages;
+          mbar_wait_bounded(&empty[s], ((c / kStages) & 1u) ^ 1u);
+          mbar_expect_tx(&full[s], kStageBytes);
+          tma_load_2d(ring + s * kStageBytes, &a_map, &full[s], kb * kBK, tm * kBM);
+          tma_load_2d(ring + s * kStageBytes + kSlabBytes, &b_map, &full[s], kb * kBK, tn * kBN);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------ MMA issuer (whole warp)
+    constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+    constexpr uint32_t idesc = umma_idesc_f16(kFmt, kBM, kBN, 0, 0);
+    const uint32_t ring_a = smem_u32(ring);
+    uint32_t c = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      mbar_wait_bounded(&acc_empty[a], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int kb = 0; kb < k_blocks; ++kb, ++c) {
+        const uint32_t s = c % kStages;
+        mbar_wait_bounded(&full[s], (c / kStages) & 1u);
+        tc_fence_after();
+        const uint32_t sa = ring_a + s * kStageBytes, sb = sa + kSlabBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBK / 16; ++ks)
+          umma_ss(tmem + a * kBN, umma_desc_sw128(sa + ks * 32, 16, 1024), umma_desc_sw128(sb + ks * 32, 16, 1024), idesc,
+                  (kb | ks) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(&acc_full[a]);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------ epilogue / reduce / copy
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // row of the tile
+    const int tid = threadIdx.x - 64;       // 0..127
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(epoch_slot);
+    const uint32_t par = epoch & 1u;
+    T* out = reinterpret_cast<T*>(p.out);
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+
+    // un-swizzle a tile image (shared or global) into out; 16 threads cover one 256-byte row: coalesced
+    auto image_to_out = [&](auto load_chunk, int tm, int tn) {
+#pragma unroll 4
+      for (int idx = tid; idx < kBM * 16; idx += kEpiThreads) {
+        const int r = idx >> 4, ch = idx & 15;
+        const int64_t gr = (int64_t)tm * kBM + r, gc = (int64_t)tn * kBN + ch * 8;
+        if (gr < p.m && gc < p.n) {
+          const uint4 v = load_chunk(image_off(r, ch));
+          T* dst = out + gr * p.out_rs + gc;
+          if (gc + 8 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(dst) = v;
+          } else {
+            const T* e = reinterpret_cast<const T*>(&v);
+            for (int i = 0; i < 8 && gc + i < p.n; ++i) dst[i] = e[i];
+          }
+        }
+      }
+    };
+
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      mbar_wait_bounded(&acc_full[a], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kBN + c4 * 32), r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]);
+          if (bias) {
+            const int64_t gc = (int64_t)tn * kBN + c4 * 32 + g * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (gc + i < p.n) f[i] += DType<T>::to_f(bias[gc + i]);
+          }
+          uint4 v;
+          v.x = pack2<T>(f[0], f[1]);
+          v.y = pack2<T>(f[2], f[3]);
+          v.z = pack2<T>(f[4], f[5]);
+          v.w = pack2<T>(f[6], f[7]);
+          *reinterpret_cast<uint4*>(image + image_off(row, c4 * 4 + g)) = v;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);  // the MMA warp may start the tile after next
+      if (p.world == 1) {
+        epi_barrier();
+        image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(image + off); }, tm, tn);
+        epi_barrier();
+      } else {
+        fence_async_smem();
+        epi_barrier();
+        if (tid == 0) {
+          if (p.one_shot) {
+            for (int d = 0; d < p.world; ++d) bulk_store(p.ws[d] + one_off(p, par, t, p.rank), image, kImageBytes);
+            tma_store_commit();
+            tma_store_wait_all();  // image read and the peer writes performed
+            for (int d = 0; d < p.world; ++d)
+              st_flag_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_one_off(p, par, t, p.rank)), epoch);
+          } else {
+            const int owner = t % p.world, local_tile = t / p.world;
+            bulk_store(p.ws[owner] + partial_off(p, par, local_tile, p.rank), image, kImageBytes);
+            tma_store_commit();
+            tma_store_wait_all();
+            st_flag_sys(reinterpret_cast<uint32_t*>(p.ws[owner] + flag_partial_off(p, par, local_tile, p.rank)), epoch);
+          }
+        }
+        epi_barrier();  // the image buffer is free again
+      }
+    }
+
+    if (p.world > 1 && p.one_shot) {
+      // ---- one-shot: every rank holds every rank's partial of every tile; this CTA sums the tiles it computed
+      // straight into `out`.  The operand ring is free (see below) and stages `world` row chunks at a time.
+      uint8_t* self = p.ws[p.rank];
+      uint32_t aux_phase = 0;
+      const int rows_per_pass = p.world <= 4 ? kBM : kBM / 2;  // world * chunk <= 128 KB of the ring
+      const uint32_t chunk_bytes = rows_per_pass * 256;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+        if (tid < p.world) wait_flag(reinterpret_cast<const uint32_t*>(self + flag_one_off(p, par, t, tid)), epoch);
+        epi_barrier();
+        for (int r0 = 0; r0 < kBM; r0 += rows_per_pass) {
+          if (tid == 0) {
+            fence_async_global();
+            mbar_expect_tx(aux_bar, chunk_bytes * p.world);
+            for (int s = 0; s < p.world; ++s)
+              bulk_load(ring + s * chunk_bytes, self + one_off(p, par, t, s) + r0 * 256, chunk_bytes, aux_bar);
+          }
+          mbar_wait_bounded(aux_bar, aux_phase);
+          aux_phase ^= 1u;
+#pragma unroll 2
+          for (int idx = tid; idx < rows_per_pass * 16; idx += kEpiThreads) {
+            const int r = r0 + (idx >> 4), ch = idx & 15;
+            const int64_t gr = (int64_t)tm * kBM + r, gc = (int64_t)tn * kBN + ch * 8;
+            if (gr < p.m && gc < p.n) {
+              const uint32_t off = image_off(r, ch) - r0 * 256;
+              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int s = 0; s < kMaxWorld; ++s)
+                if (s < p.world) acc2<T>(acc, *reinterpret_cast<const uint4*>(ring + s * chunk_bytes + off));
+              uint4 v;
+              v.x = pack2<T>(acc[0], acc[1]);
+              v.y = pack2<T>(acc[2], acc[3]);
+              v.z = pack2<T>(acc[4], acc[5]);
+              v.w = pack2<T>(acc[6], acc[7]);
+              T* dst = out + gr * p.out_rs + gc;
+              if (gc + 8 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                *reinterpret_cast<uint4*>(dst) = v;
+              } else {
+                const T* e = reinterpret_cast<const T*>(&v);
+                for (int i = 0; i < 8 && gc + i < p.n; ++i) dst[i] = e[i];
+              }
+            }
+          }
+          epi_barrier();  // the ring chunk buffers are free again
+        }
+      }
+    } else if (p.world > 1) {
+      // every MMA that read the operand ring has completed (the last acc_full commit was observed above) and the
+      // producer has nothing left to load: the ring is free, its first 64 KB stage the bulk loads below
+      uint8_t* self = p.ws[p.rank];
+      uint8_t* red_in = ring;                 // `world` partial slabs (32 KB in total)
+      uint8_t* copy_in = ring + kImageBytes;  // one result image
+      uint32_t aux_phase = 0;
+      // ---- reduce units: (owned tile, row slab); unit u of this rank goes to CTA u % gridDim.x
+      const int owned = (p.n_tiles - p.rank + p.world - 1) / p.world;  // tiles t with t % world == rank
+      const uint32_t slab_bytes = kImageBytes / p.world;
+      for (int u = blockIdx.x; u < owned * p.world; u += gridDim.x) {
+        const int local_tile = u / p.world, slab = u - local_tile * p.world;
+        const int t = local_tile * p.world + p.rank;
+        if (tid < p.world)
+          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_partial_off(p, par, local_tile, tid)), epoch);
+        epi_barrier();
+        if (tid == 0) {
+          fence_async_global();
+          mbar_expect_tx(aux_bar, kImageBytes);
+          for (int s = 0; s < p.world; ++s)
+            bulk_load(red_in + s * slab_bytes, self + partial_off(p, par, local_tile, s) + slab * slab_bytes, slab_bytes,
+                      aux_bar);
+        }
+        mbar_wait_bounded(aux_bar, aux_phase);
+        aux_phase ^= 1u;
+        for (uint32_t off = tid * 16; off < slab_bytes; off += kEpiThreads * 16) {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int s = 0; s < kMaxWorld; ++s)
+            if (s < p.world) acc2<T>(acc, *reinterpret_cast<const uint4*>(red_in + s * slab_bytes + off));
+          uint4 o;
+          o.x = pack2<T>(acc[0], acc[1]);
+          o.y = pack2<T>(acc[2], acc[3]);
+          o.z = pack2<T>(acc[4], acc[5]);
+          o.w = pack2<T>(acc[6], acc[7]);
+          *reinterpret_cast<uint4*>(image + off) = o;
+        }
+        fence_async_smem();
+        epi_barrier();
+        if (tid == 0) {
+          const size_t dst = result_off(p, par, t) + (size_t)slab * slab_bytes;
+          for (int d = 0; d < p.world; ++d) bulk_store(p.ws[d] + dst, image, slab_bytes);
+          tma_store_commit();
+          tma_store_wait_all();
+          for (int d = 0; d < p.world; ++d)
+            st_flag_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_result_off(p, par, t, slab)), epoch);
+        }
+        epi_barrier();  // image and red_in are free again
+      }
+      // ---- copy units: the tiles this CTA computed
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+        if (tid < p.world)
+          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_result_off(p, par, t, tid)), epoch);
+        epi_barrier();
+        if (tid == 0) {
+          fence_async_global();
+          mbar_expect_tx(aux_bar, kImageBytes);
+          bulk_load(copy_in, self + result_off(p, par, t), kImageBytes, aux_bar);
+        }
+        mbar_wait_bounded(aux_bar, aux_phase);
+        aux_phase ^= 1u;
+        image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(copy_in + off); }, tm, tn);
+        epi_barrier();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+  if (p.world > 1 && threadIdx.x == 0) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(p.ws[p.rank]);
+    __threadfence();
+    if (atomicAdd(hdr + 1, 1u) == gridDim.x - 1) {
+      hdr[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(hdr) = *reinterpret_cast<volatile uint32_t*>(epoch_slot);
+    }
+  }
+}
+
+static int build_2d_map(const void* base, int dtype, int64_t rows, int64_t cols, int64_t row_stride, CUtensorMap* out) {
+  TensorMapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = 2;
+  key.dtype = dtype;
+  key.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  key.dims[0] = (uint64_t)cols;  key.box[0] = kBK;
+  key.dims[1] = (uint64_t)rows;  key.strides[0] = (uint64_t)row_stride * 2;  key.box[1] = kBM;
+  return get_tensor_map(key, out);
+}
+
+}  // namespace gar
+}  // namespace mojo
+
+using namespace mojo;
+
+extern "C" int mojo_b200_symm_alloc(size_t bytes, void** ptr) {
+  MOJO_REQUIRE(ptr && bytes > 0, MOJO_B200_EINVAL, "symm_alloc: bad arguments");
+  MOJO_CUDA_OK(cudaMalloc(ptr, bytes));
+  MOJO_CUDA_OK(cudaMemset(*ptr, 0, bytes));
+  MOJO_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int mojo_b200_symm_free(void* ptr) {
+  if (ptr) MOJO_CUDA_OK(cudaFree(ptr));
+  return 0;
+}
+
+extern "C" int mojo_b200_symm_export(void* ptr, void* handle64) {
+  MOJO_REQUIRE(ptr && handle64, MOJO_B200_EINVAL, "symm_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  MOJO_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+
+extern "C" int mojo_b200_symm_open(const void* handle64, void** peer_ptr) {
+  MOJO_REQUIRE(handle64 && peer_ptr, MOJO_B200_EINVAL, "symm_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  MOJO_CUDA_OK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int mojo_b200_symm_close(void* peer_ptr) {
+  if (peer_ptr) MOJO_CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
+  return 0;
+}
+
+extern "C" size_t mojo_b200_gemm_allreduce_workspace_bytes(int64_t max_m, int64_t n, int world) {
+  if (max_m <= 0 || n <= 0 || world < 1 || world > gar::kMaxWorld || (world & (world - 1))) return 0;
+  if (world == 1) return 0;
+  return gar::make_layout(max_m, n, world).total;
+}
+
+extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const void* bias, void* out, int64_t m,
+                                        int64_t n, int64_t k, int64_t x_row_stride, int64_t w_row_stride,
+                                        int64_t out_row_stride, void* const* peer_workspaces, size_t workspace_bytes,
+                                        int64_t workspace_max_m, int world, int rank, int dtype, void* stream) {
+  using namespace gar;
+  MOJO_REQUIRE(m >= 0 && n > 0 && k > 0, MOJO_B200_EINVAL, "gemm_allreduce: bad sizes");
+  MOJO_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, MOJO_B200_EINVAL,
+               "gemm_allreduce: bad world/rank %d/%d", rank, world);
+  MOJO_REQUIRE((world & (world - 1)) == 0, MOJO_B200_EUNSUPPORTED, "gemm_allreduce: world %d must be 1, 2, 4 or 8", world);
+  MOJO_REQUIRE(dtype == MOJO_B200_BF16 || dtype == MOJO_B200_F16, MOJO_B200_EUNSUPPORTED,
+               "gemm_allreduce: bf16/fp16 only (tensor-core path)");
+  if (m == 0) return 0;  // nothing to compute, and every rank sees the same m: nothing to exchange either
+  MOJO_REQUIRE(x && weight && out, MOJO_B200_EINVAL, "gemm_allreduce: null tensor pointer");
+  MOJO_REQUIRE(x_row_stride % 8 == 0 && w_row_stride % 8 == 0 && aligned16(x) && aligned16(weight), MOJO_B200_EUNSUPPORTED,
+               "gemm_allreduce: x / weight rows must be 16-byte aligned (TMA)");
+  MOJO_REQUIRE(x_row_stride >= k && w_row_stride >= k && out_row_stride >= n, MOJO_B200_EINVAL,
+               "gemm_allreduce: row strides smaller than the row");
+  MOJO_REQUIRE(m < (1LL << 31) && n < (1LL << 31) && k < (1LL << 31), MOJO_B200_EUNSUPPORTED, "gemm_allreduce: too large");
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.out = out; p.bias = bias; p.m = m; p.n = n; p.k = k; p.out_rs = out_row_stride;
+  p.tiles_m = (int)((m + kBM - 1) / kBM);
+  p.tiles_n = (int)((n + kBN - 1) / kBN);
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  MOJO_REQUIRE(tiles < (1LL << 30), MOJO_B200_EUNSUPPORTED, "gemm_allreduce: too many tiles");
+  p.n_tiles = (int)tiles;
+  p.world = world; p.rank = rank;
+  if (world > 1) {
+    MOJO_REQUIRE(peer_workspaces, MOJO_B200_EINVAL, "gemm_allreduce: peer workspace table is null");
+    MOJO_REQUIRE(workspace_max_m >= m, MOJO_B200_EWORKSPACE, "gemm_allreduce: m %lld exceeds the workspace's max_m %lld",
+                 (long long)m, (long long)workspace_max_m);
+    const Layout l = make_layout(workspace_max_m, n, world);
+    MOJO_REQUIRE(workspace_bytes >= l.total, MOJO_B200_EWORKSPACE, "gemm_allreduce: workspace %zu < %zu bytes",
+                 workspace_bytes, l.total);
+    p.owned_cap = l.owned_cap; p.tiles_cap = l.tiles_cap;
+    p.off_partial = l.off_partial; p.off_result = l.off_result;
+    p.off_flag_partial = l.off_flag_partial; p.off_flag_result = l.off_flag_result;
+    p.one_cap = l.one_cap; p.off_one = l.off_one; p.off_flag_one = l.off_flag_one;
+    // one-shot (push to everyone, reduce locally: one NVLink hop) while the extra traffic is cheap; two-shot
+    // (push to the owner, reduce, broadcast: two hops, 1/world of the bytes per hop) beyond
+    const char* mode = getenv("MOJO_B200_GAR_MODE");  // "one" / "two" force a mode (both ranks alike!)
+    p.one_shot = p.n_tiles <= l.one_cap && (size_t)(world - 1) * m * n * 2 <= kOneShotMaxPeerBytes;
+    if (mode && !strcmp(mode, "two")) p.one_shot = 0;
+    if (mode && !strcmp(mode, "one") && p.n_tiles <= l.one_cap) p.one_shot = 1;
+    for (int r = 0; r < world; ++r) {
+      MOJO_REQUIRE(peer_workspaces[r], MOJO_B200_EINVAL, "gemm_allreduce: workspace of rank %d is null", r);
+      p.ws[r] = reinterpret_cast<uint8_t*>(peer_workspaces[r]);
+    }
+  }
+
+  CUtensorMap a_map, b_map;
+  int rc = build_2d_map(x, dtype, m, k, x_row_stride, &a_map);
+  if (rc != 0) return rc;
+  rc = build_2d_map(weight, dtype, n, k, w_row_stride, &b_map);
+  if (rc != 0) return rc;
+
+  const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == MOJO_B200_BF16) {
+    auto kern = gemm_allreduce_kernel<__nv_bfloat16>;
+    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    kern<<<grid, kThreads, kSmemBytes, s>>>(a_map, b_map, p);
+  } else {
+    auto kern = gemm_allreduce_kernel<__half>;
+    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    kern<<<grid, kThreads, kSmemBytes, s>>>(a_map, b_map, p);
+  }
+  return check_launch("gemm_allreduce_kernel");
+}

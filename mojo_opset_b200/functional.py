@@ -423,3 +423,45 @@ def sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Opt
         float(scale), _lib.dtype_id(query.dtype), _lib.stream_ptr(dev))
     _lib.check(lib, rc, "sdpa")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# MojoGemmAllReduce
+# ------------------------------------------------------------------------------------------------------
+def gemm_allreduce_workspace_bytes(max_m: int, n: int, world: int) -> int:
+    return int(_lib.load().mojo_b200_gemm_allreduce_workspace_bytes(int(max_m), int(n), int(world)))
+
+
+def gemm_allreduce(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, workspace=None,
+                   workspace_max_m: int = 0) -> torch.Tensor:
+    """``all_reduce_sum(x @ weight.T + bias)`` in one kernel.  ``weight`` is ``[out_features, in_features_local]``;
+    ``workspace`` is a ``comm.SymmetricWorkspace`` (or a ``comm.LocalRanks`` view) sized by
+    ``gemm_allreduce_workspace_bytes(workspace_max_m, out_features, world)``; ``None`` = single rank, plain GEMM."""
+    dev = _require_cuda(x, weight, bias)
+    lib = _lib.load()
+    if x.dtype != weight.dtype or (bias is not None and bias.dtype != x.dtype):
+        raise NotImplementedError("gemm_allreduce: input, weight and bias must share one dtype")
+    if weight.dim() != 2 or x.shape[-1] != weight.shape[1]:
+        raise ValueError(f"gemm_allreduce: input {tuple(x.shape)} does not match weight {tuple(weight.shape)}")
+    n, k = weight.shape
+    if bias is not None and tuple(bias.shape) != (n,):
+        raise ValueError(f"gemm_allreduce: bias shape {tuple(bias.shape)} != ({n},)")
+    x2 = _as_rows(x)
+    w = weight if weight.stride(1) == 1 else weight.contiguous()
+    if x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    if (w.stride(0) % 8 or w.data_ptr() % 16) and k % 8 == 0:
+        w = w.contiguous()
+    m = x2.shape[0]
+    out = torch.empty((m, n), dtype=x.dtype, device=dev)
+    b = None if bias is None else bias.contiguous()
+    world = 1 if workspace is None else workspace.world
+    if world > 1:
+        table, ws_bytes, rank = workspace.table, workspace.nbytes, workspace.rank
+    else:
+        table, ws_bytes, rank = None, 0, 0
+    rc = lib.mojo_b200_gemm_allreduce(
+        x2.data_ptr(), w.data_ptr(), _lib.ptr(b), out.data_ptr(), m, n, k, x2.stride(0), w.stride(0), out.stride(0),
+        table, ws_bytes, int(workspace_max_m), world, rank, _lib.dtype_id(x.dtype), _lib.stream_ptr(dev))
+    _lib.check(lib, rc, "gemm_allreduce")
+    return out.view(*x.shape[:-1], n)

@@ -271,3 +271,35 @@ def swiglu(gate_out, up_out, swiglu_limit: float = 0.0):
         up_out = torch.clamp(up_out, min=-swiglu_limit, max=swiglu_limit)
         gate_out = torch.clamp(gate_out, max=swiglu_limit)
     return F.silu(gate_out) * up_out
+
+
+# --------------------------------------------------------------------------------------------------
+# f1  MojoGemmAllReduce                          reference core/operators/compute_with_comm.py:12-24,57-117
+# --------------------------------------------------------------------------------------------------
+def gemm(input, weight, bias=None, trans_weight: bool = False):
+    """The rank-local projection (compute_with_comm.py:12-24): ``input @ weight (+ bias)`` or ``F.linear``."""
+    if trans_weight:
+        output = input @ weight
+        if bias is not None:
+            output = output + bias
+        return output
+    return F.linear(input, weight, bias)
+
+
+def gemm_allreduce(input, weight, bias=None, trans_weight: bool = False, process_group=None):
+    """``all_reduce_sum(gemm(...))`` over ``process_group``; identity reduction without an initialised group
+    (compute_with_comm.py:111-117)."""
+    import torch.distributed as dist
+
+    output = gemm(input, weight, bias, trans_weight)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(output, op=dist.ReduceOp.SUM, group=process_group)
+    return output
+
+
+def gemm_allreduce_emulated(inputs, weights, biases=None, trans_weight: bool = False):
+    """Single-process statement of the same result for a list of per-rank shards: every rank's projection is
+    materialised in the input dtype (as ``F.linear`` does), the all-reduce then sums those tensors."""
+    parts = [gemm(x, w, None if biases is None else biases[r], trans_weight)
+             for r, (x, w) in enumerate(zip(inputs, weights))]
+    return torch.stack([p.float() for p in parts]).sum(0).to(parts[0].dtype)

@@ -101,3 +101,10 @@ class TorchSwiGLU(core.MojoSwiGLU):
 
     def forward(self, gate_out, up_out):
         return golden.swiglu(gate_out, up_out, self.swiglu_limit)
+
+
+class TorchGemmAllReduce(core.MojoGemmAllReduce):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, input):
+        return golden.gemm_allreduce(input, self.weight, self.bias, self.trans_weight, self.process_group)
