@@ -221,6 +221,32 @@ MOJO_B200_API int mojo_b200_gemm_allreduce(
     void* const* peer_workspaces, size_t workspace_bytes, int64_t workspace_max_m,
     int world, int rank, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Fused pre-attention pass: per-head RMSNorm (optional) -> RoPE -> paged KV store, one HBM pass.
+ * Op shells MojoRoPEStoreKV / MojoNormRoPEStoreKV (reference README.md:128-130); today's composition is
+ * modeling/qwen3/mojo_qwen3_dense.py:229-234 (q_norm, k_norm, rope) + PagedDummyCache.update :99-109
+ * (MojoStorePagedKVCache) = four launches and a host-built plan.
+ *
+ * q [T, Hq, D], k / v [T, Hkv, D] (strides t, h; e.g. views of one fused QKV projection), norm weights [D] or
+ * both NULL (no norm), cos / sin [T, rope_dim] (fp32 or the tensors' dtype, row stride cos_stride_t; the
+ * rotation covers the LAST rope_dim features) -> q_out [T, Hq, D]; k' and v go to the page slot of their token,
+ * found from (block_table, cu_q_lens | NULL = decode, context_kv_lens) as in store_paged_kv_table; k_out
+ * (optional, [T, Hkv, D]) also receives k'.  bf16 / fp16, D in {64, 128, 256}.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_norm_rope_store_kv(
+    const void* q, const void* k, const void* v, const void* q_norm_weight, const void* k_norm_weight, float eps,
+    const void* cos, const void* sin, void* q_out, void* k_out, void* key_cache, void* value_cache,
+    const int32_t* block_table, int64_t table_stride, int max_blocks_per_seq,
+    const int32_t* cu_q_lens, const int32_t* context_kv_lens, int num_seqs,
+    int64_t num_tokens, int num_q_heads, int num_kv_heads, int head_dim, int rope_dim,
+    int64_t num_blocks, int block_size,
+    int64_t q_stride_t, int64_t q_stride_h, int64_t k_stride_t, int64_t k_stride_h,
+    int64_t v_stride_t, int64_t v_stride_h, int64_t qo_stride_t, int64_t qo_stride_h,
+    int64_t ko_stride_t, int64_t ko_stride_h, int64_t cos_stride_t,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    int dtype, int cos_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ from .operators.attention import B200PagedDecodeGQA
 from .operators.attention import B200PagedPrefillGQA
 from .operators.attention import B200Sdpa
 from .operators.compute_with_comm import B200GemmAllReduce
+from .operators.fused_attention_input import B200NormRoPEStoreKV
+from .operators.fused_attention_input import B200RoPEStoreKV
 from .operators.kv_cache import B200StorePagedKVCache
 from .operators.normalization import B200ResidualAddRMSNorm
 from .operators.normalization import B200RMSNorm
@@ -19,6 +21,8 @@ __all__ = [
     "B200PagedPrefillGQA",
     "B200Sdpa",
     "B200GemmAllReduce",
+    "B200NormRoPEStoreKV",
+    "B200RoPEStoreKV",
     "B200StorePagedKVCache",
     "B200ResidualAddRMSNorm",
     "B200RMSNorm",

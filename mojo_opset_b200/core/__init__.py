@@ -9,6 +9,8 @@ from .operators.attention import MojoPagedDecodeGQA
 from .operators.attention import MojoPagedPrefillGQA
 from .operators.attention import MojoSdpa
 from .operators.compute_with_comm import MojoGemmAllReduce
+from .operators.fused_attention_input import MojoNormRoPEStoreKV
+from .operators.fused_attention_input import MojoRoPEStoreKV
 from .operators.kv_cache import MojoStorePagedKVCache
 from .operators.kv_cache import build_paged_kv_chunk_metadata
 from .operators.normalization import MojoResidualAddRMSNorm
@@ -25,6 +27,8 @@ __all__ = [
     "MojoPagedPrefillGQA",
     "MojoSdpa",
     "MojoGemmAllReduce",
+    "MojoNormRoPEStoreKV",
+    "MojoRoPEStoreKV",
     "MojoStorePagedKVCache",
     "build_paged_kv_chunk_metadata",
     "MojoResidualAddRMSNorm",

@@ -465,3 +465,58 @@ def gemm_allreduce(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
         table, ws_bytes, int(workspace_max_m), world, rank, _lib.dtype_id(x.dtype), _lib.stream_ptr(dev))
     _lib.check(lib, rc, "gemm_allreduce")
     return out.view(*x.shape[:-1], n)
+
+
+# ------------------------------------------------------------------------------------------------------
+# MojoNormRoPEStoreKV / MojoRoPEStoreKV
+# ------------------------------------------------------------------------------------------------------
+def norm_rope_store_kv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
+                       key_cache: torch.Tensor, value_cache: torch.Tensor, block_table: torch.Tensor,
+                       cu_q_lens: Optional[torch.Tensor], context_kv_lens: torch.Tensor,
+                       q_norm_weight: Optional[torch.Tensor] = None, k_norm_weight: Optional[torch.Tensor] = None,
+                       eps: float = 1e-6, want_k: bool = False):
+    """One pass: optional per-head RMSNorm of q and k, RoPE on both, k / v scattered into their page slots.
+    ``q, k, v`` are token-major ``[T, heads, D]`` (any token / head strides); returns ``q_rot`` (and ``k_rot`` when
+    ``want_k``); the caches are updated in place."""
+    dev = _require_cuda(q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens, context_kv_lens,
+                        q_norm_weight, k_norm_weight)
+    lib = _lib.load()
+    if q.dim() != 3 or k.dim() != 3 or v.dim() != 3 or k.shape != v.shape or q.shape[0] != k.shape[0]:
+        raise ValueError("norm_rope_store_kv: q [T,Hq,D], k/v [T,Hkv,D] expected")
+    if not (q.dtype == k.dtype == v.dtype == key_cache.dtype == value_cache.dtype):
+        raise NotImplementedError("norm_rope_store_kv: q, k, v and the caches must share one dtype")
+    if key_cache.dim() != 4 or key_cache.shape != value_cache.shape:
+        raise ValueError("norm_rope_store_kv: caches must be [num_blocks, kv_heads, block_size, head_dim]")
+    tokens, hq, d = q.shape
+    hkv = k.shape[1]
+    num_blocks, c_heads, block_size, c_d = key_cache.shape
+    if (c_heads, c_d) != (hkv, d) or q.shape[2] != d:
+        raise ValueError("norm_rope_store_kv: head counts / head_dim of states and caches differ")
+    if key_cache.stride(-1) != 1 or value_cache.stride(-1) != 1:
+        raise NotImplementedError("norm_rope_store_kv: cache head_dim must be contiguous (in-place op)")
+    if (q_norm_weight is None) != (k_norm_weight is None):
+        raise ValueError("norm_rope_store_kv: give both norm weights or neither")
+    q, k, v = _inner_contiguous(q), _inner_contiguous(k), _inner_contiguous(v)
+    if cos.dim() != 2 or cos.shape[0] != tokens or sin.shape != cos.shape:
+        raise ValueError("norm_rope_store_kv: cos/sin must be [T, rope_dim]")
+    if cos.stride(-1) != 1 or sin.stride() != cos.stride() or sin.dtype != cos.dtype:
+        cos, sin = cos.contiguous(), sin.contiguous().to(cos.dtype)
+    table = block_table if block_table.stride(-1) == 1 or block_table.shape[1] <= 1 else block_table.contiguous()
+    ctx = context_kv_lens.contiguous()
+    cu = None if cu_q_lens is None else cu_q_lens.contiguous()
+    wq = None if q_norm_weight is None else q_norm_weight.detach().contiguous()
+    wk = None if k_norm_weight is None else k_norm_weight.detach().contiguous()
+    q_out = torch.empty((tokens, hq, d), dtype=q.dtype, device=dev)
+    k_out = torch.empty((tokens, hkv, d), dtype=q.dtype, device=dev) if want_k else None
+    rc = lib.mojo_b200_norm_rope_store_kv(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), _lib.ptr(wq), _lib.ptr(wk), float(eps), cos.data_ptr(),
+        sin.data_ptr(), q_out.data_ptr(), _lib.ptr(k_out), key_cache.data_ptr(), value_cache.data_ptr(),
+        table.data_ptr(), table.stride(0) if table.shape[1] else 0, table.shape[1], _lib.ptr(cu), ctx.data_ptr(),
+        ctx.shape[0], tokens, hq, hkv, d, cos.shape[-1], num_blocks, block_size,
+        q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), q_out.stride(0), q_out.stride(1),
+        k_out.stride(0) if want_k else 0, k_out.stride(1) if want_k else 0, cos.stride(0),
+        key_cache.stride(0), key_cache.stride(1), key_cache.stride(2),
+        value_cache.stride(0), value_cache.stride(1), value_cache.stride(2),
+        _lib.dtype_id(q.dtype), _lib.dtype_id(cos.dtype), _lib.stream_ptr(dev))
+    _lib.check(lib, rc, "norm_rope_store_kv")
+    return (q_out, k_out) if want_k else q_out

@@ -303,3 +303,18 @@ def gemm_allreduce_emulated(inputs, weights, biases=None, trans_weight: bool = F
     parts = [gemm(x, w, None if biases is None else biases[r], trans_weight)
              for r, (x, w) in enumerate(zip(inputs, weights))]
     return torch.stack([p.float() for p in parts]).sum(0).to(parts[0].dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# f2  MojoRoPEStoreKV / MojoNormRoPEStoreKV: the composition the reference's Qwen3 block performs with four ops
+#     (modeling/qwen3/mojo_qwen3_dense.py:229-234 + PagedDummyCache.update :99-109)
+# --------------------------------------------------------------------------------------------------
+def norm_rope_store_kv(q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens, context_kv_lens,
+                       q_weight=None, k_weight=None, eps: float = 1e-6):
+    """Token-major ``[T, heads, D]`` tensors.  Returns ``(q_rot, k_rot)``; the caches are updated in place."""
+    if q_weight is not None:
+        q, k = rms_norm(q, q_weight, eps), rms_norm(k, k_weight, eps)
+    q_rot, k_rot = apply_rope(q, k, cos, sin, head_first=False)
+    plan = build_chunk_plan(block_table, cu_q_lens, context_kv_lens, key_cache.shape[2])
+    store_paged_kv(k_rot, v, key_cache, value_cache, plan)
+    return q_rot, k_rot

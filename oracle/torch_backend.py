@@ -108,3 +108,19 @@ class TorchGemmAllReduce(core.MojoGemmAllReduce):
 
     def forward(self, input):
         return golden.gemm_allreduce(input, self.weight, self.bias, self.trans_weight, self.process_group)
+
+
+class TorchRoPEStoreKV(core.MojoRoPEStoreKV):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens, context_kv_lens):
+        return golden.norm_rope_store_kv(q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens,
+                                         context_kv_lens)[0]
+
+
+class TorchNormRoPEStoreKV(core.MojoNormRoPEStoreKV):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens, context_kv_lens):
+        return golden.norm_rope_store_kv(q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens,
+                                         context_kv_lens, self.q_weight, self.k_weight, self.variance_epsilon)[0]

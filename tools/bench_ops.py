@@ -131,6 +131,25 @@ def bench_elementwise(rows_list):
         us = time_us([lambda s=s: F.store_paged_kv(s[0], s[1], s[2], s[3], chunk_metadata=s[4]) for s in sets])
         out.append(("store_paged_kv", f"T={T} chunks={chunks}", nbytes, us))
         del sets
+        # fused q/k-norm + RoPE + KV store (one pass): reads q, k, v, writes q' and the k', v slots
+        nbytes = (2 * Hq + 4 * Hkv) * D * 2 * T + 2 * T * D * 4 + 2 * D * 2
+        n = copies_for(nbytes)
+        sets = []
+        for _ in range(n):
+            if prefill:
+                table = torch.randperm(nb)[: T // bs].view(1, -1).to(torch.int32).to(DEV)
+                cu = torch.tensor([0, T], dtype=torch.int32, device=DEV)
+                ctx = torch.zeros(1, dtype=torch.int32, device=DEV)
+            else:
+                table = torch.randperm(nb)[:T].view(T, 1).to(torch.int32).to(DEV)
+                cu, ctx = None, torch.full((T,), 5, dtype=torch.int32, device=DEV)
+            sets.append((rnd(T, Hq, D), rnd(T, Hkv, D), rnd(T, Hkv, D), rnd(T, D, dtype=torch.float32),
+                         rnd(T, D, dtype=torch.float32), rnd(nb, Hkv, bs, D), rnd(nb, Hkv, bs, D), table, cu, ctx))
+        wq, wk = rnd(D), rnd(D)
+        us = time_us([lambda s=s: F.norm_rope_store_kv(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9],
+                                                        wq, wk, 1e-6) for s in sets])
+        out.append(("norm_rope_store_kv (fused)", f"T={T} {Hq}q+{Hkv}k+{Hkv}v heads", nbytes, us))
+        del sets
         torch.cuda.empty_cache()
     return out
 
@@ -182,10 +201,10 @@ def main():
         rows += bench_decode()
     table = []
     print(f"HBM peak {peak:.0f} GB/s ({src})")
-    print(f"{'op':24s} {'shape':42s} {'MB':>9s} {'us':>9s} {'GB/s':>8s} {'frac':>6s} {'eager us':>9s}")
+    print(f"{'op':28s} {'shape':42s} {'MB':>9s} {'us':>9s} {'GB/s':>8s} {'frac':>6s} {'eager us':>9s}")
     for op, shape, nbytes, (us, eager) in rows:
         gbs = nbytes / us / 1e3
-        print(f"{op:24s} {shape:42s} {nbytes / 1e6:9.2f} {us:9.1f} {gbs:8.0f} {gbs / peak:6.2f} {eager:9.1f}")
+        print(f"{op:28s} {shape:42s} {nbytes / 1e6:9.2f} {us:9.1f} {gbs:8.0f} {gbs / peak:6.2f} {eager:9.1f}")
         table.append(dict(op=op, shape=shape, algorithmic_bytes=nbytes, us=us, gbs=gbs, frac=gbs / peak,
                           eager_us=eager))
     if args.json:
