@@ -35,6 +35,7 @@ OPS = (
     "RotaryEmbedding",
     "SwiGLU",
     "Silu",
+    "GemmAllReduce",
 )
 
 
@@ -72,7 +73,11 @@ def register(upstream=None) -> Dict[str, type]:
             "supported_platforms_list": [platform],
             "forward": our_cls.forward,
         }
-        # argument-check helpers our forward() calls on self (defined on this package's mirror of the core op)
+        # private helpers of our backend class itself (lazy state, workspaces) ...
+        for name, attr in vars(our_cls).items():
+            if name.startswith("_") and not name.startswith("__") and callable(attr):
+                namespace.setdefault(name, attr)
+        # ... and argument-check helpers our forward() calls on self (defined on this package's mirror of the core op)
         for base in our_cls.__mro__[1:]:
             for name, attr in vars(base).items():
                 if name.startswith("_check_") and callable(attr) and not hasattr(core_cls, name):

@@ -86,6 +86,28 @@ def _worker(rank, world, port, mode, out_queue):
                                             vc[:, s.kv_begin:s.kv_end].contiguous(), lens, table)
             y = RowParallelOutProj(w_o, s, D)(local)  # the one collective on the path
             ok = torch.allclose(y, full, atol=1e-4, rtol=1e-4)
+        elif mode == "gemm_allreduce":
+            # MojoGemmAllReduce through the registry with the oracle backend under gloo: the o_proj of the TP block as
+            # the reference's fused op (core/operators/compute_with_comm.py:57-117), bias added on every rank
+            import mojo_opset_b200 as mj
+            import oracle.torch_backend  # noqa: F401  registers backend "torch"
+
+            os.environ["MOJO_BACKEND"] = "torch"
+            s = shard_heads(Hq, Hkv, world, rank)
+            w_local = w_o[:, s.q_begin * D: s.q_end * D].contiguous()
+            bias = torch.arange(w_o.shape[0], dtype=torch.float32) / 10
+            x_local = full_attn[:, s.q_begin:s.q_end].reshape(B, -1)
+            op = mj.MojoGemmAllReduce(w_local, bias, trans_weight=False)
+            op_t = mj.MojoGemmAllReduce(w_local.t().contiguous(), bias, trans_weight=True)
+            y, y_t = op(x_local), op_t(x_local)
+            ok = (type(op).__name__ == "TorchGemmAllReduce" and torch.allclose(y, full + world * bias, atol=1e-4, rtol=1e-4)
+                  and torch.allclose(y_t, y, atol=1e-5, rtol=1e-5))
+            emu = golden.gemm_allreduce_emulated(
+                [full_attn[:, shard_heads(Hq, Hkv, world, r).q_begin:shard_heads(Hq, Hkv, world, r).q_end].reshape(B, -1)
+                 for r in range(world)],
+                [w_o[:, shard_heads(Hq, Hkv, world, r).q_begin * D: shard_heads(Hq, Hkv, world, r).q_end * D]
+                 for r in range(world)], [bias] * world)
+            ok = ok and torch.allclose(emu, y, atol=1e-5, rtol=1e-5)
         else:  # data parallel: every rank owns a contiguous share of the sequences, no collective on the data path
             b0, b1 = shard_range(B, world, rank)
             local = golden.paged_decode_gqa(q[b0:b1], kc, vc, lens[b0:b1], table[b0:b1])
@@ -98,7 +120,7 @@ def _worker(rank, world, port, mode, out_queue):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["tp", "dp"])
+@pytest.mark.parametrize("mode", ["tp", "dp", "gemm_allreduce"])
 def test_world_size_2_gloo(mode):
     world = 2
     ctx = mp.get_context("spawn")
