@@ -247,6 +247,22 @@ MOJO_B200_API int mojo_b200_norm_rope_store_kv(
     int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
     int dtype, int cos_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * DiT block, non-GEMM ops around MojoSdpa (modeling/wan2_2/mojo_wan_model.py):
+ *   MojoGelu.forward        mojo_opset/core/operators/activation.py:6-17      exact (erf) GELU
+ *   MojoLayerNorm.forward   mojo_opset/core/operators/normalization.py:19-66  F.layer_norm, weight / bias may be NULL
+ *   MojoGridRoPE.forward    mojo_opset/experimental/operators/position_embedding.py:80-118, ONE sample per call:
+ *       x [tokens, heads, D] as interleaved (re, im) pairs; phase [seq_len, D/2] complex64 viewed as fp32
+ *       (cos, sin) pairs with row stride phase_stride_t (floats); tokens >= seq_len are copied unchanged.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_gelu(const void* x, void* out, int64_t rows, int64_t cols, int64_t x_row_stride,
+                   int64_t out_row_stride, int dtype, void* stream);
+MOJO_B200_API int mojo_b200_layer_norm(const void* x, const void* weight, const void* bias, void* y, int64_t rows,
+                         int hidden, int64_t x_row_stride, int64_t y_row_stride, float eps, int dtype, void* stream);
+MOJO_B200_API int mojo_b200_grid_rope(const void* x, const float* phase, void* out, int64_t seq_len, int64_t tokens,
+                        int heads, int head_dim, int64_t x_stride_t, int64_t x_stride_h,
+                        int64_t o_stride_t, int64_t o_stride_h, int64_t phase_stride_t, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

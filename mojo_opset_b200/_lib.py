@@ -47,6 +47,9 @@ SIGNATURES = {
     "mojo_b200_sdpa": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, I, P]),
     "mojo_b200_norm_rope_store_kv": (I, [P, P, P, P, P, F, P, P, P, P, P, P, P, L, I, P, P, I, L, I, I, I, I, L, I]
                                      + [L] * 17 + [I, I, P]),
+    "mojo_b200_gelu": (I, [P, P, L, L, L, L, I, P]),
+    "mojo_b200_layer_norm": (I, [P, P, P, P, L, I, L, L, F, I, P]),
+    "mojo_b200_grid_rope": (I, [P, P, P, L, L, I, I, L, L, L, L, L, I, P]),
     "mojo_b200_symm_alloc": (I, [Z, ctypes.POINTER(c_void_p)]),
     "mojo_b200_symm_free": (I, [P]),
     "mojo_b200_symm_export": (I, [P, P]),

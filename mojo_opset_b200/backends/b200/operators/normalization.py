@@ -1,6 +1,7 @@
 import torch
 
 from mojo_opset_b200 import functional as F
+from mojo_opset_b200.core import MojoLayerNorm
 from mojo_opset_b200.core import MojoResidualAddRMSNorm
 from mojo_opset_b200.core import MojoRMSNorm
 
@@ -20,3 +21,10 @@ class B200ResidualAddRMSNorm(MojoResidualAddRMSNorm):
         y, summed = F.residual_add_rms_norm(hidden_state, residual, self.weight, self.variance_epsilon, want_sum=pre)
         # "post" returns the normalised tensor twice (reference normalization.py:350-359)
         return (y, summed) if pre else (y, y)
+
+
+class B200LayerNorm(MojoLayerNorm):
+    supported_platforms_list = ["b200"]
+
+    def forward(self, hidden_state: torch.Tensor) -> torch.Tensor:
+        return F.layer_norm(hidden_state, self.weight, self.bias, self.variance_epsilon)

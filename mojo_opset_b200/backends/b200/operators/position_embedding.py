@@ -2,6 +2,7 @@ import torch
 
 from mojo_opset_b200 import functional as F
 from mojo_opset_b200.core import MojoApplyRoPE
+from mojo_opset_b200.core import MojoGridRoPE
 from mojo_opset_b200.core import MojoRotaryEmbedding
 
 
@@ -30,3 +31,14 @@ class B200RotaryEmbedding(MojoRotaryEmbedding):
                                     self.attention_scaling, position_ids=position_ids.reshape(-1), **table)
         seq = x.shape[1]  # padded prefill [B, S, H] -> [S, d]
         return F.rotary_cos_sin(seq, (seq,), inv_freq, self.attention_scaling, period=seq, **table)
+
+
+class B200GridRoPE(MojoGridRoPE):
+    supported_platforms_list = ["b200"]
+
+    def forward(self, x, grid_sizes, freqs_list):
+        # a sample's sequence length F*H*W is the length of its phase table: no host read of grid_sizes
+        assert x.dim() == 4, "x must be 4D: [B, L, N, D]"
+        assert x.size(-1) % 2 == 0, "D must be even for complex pairing"
+        assert grid_sizes.dim() == 2 and grid_sizes.size(1) == 3, "grid_sizes must be [B, 3]"
+        return F.grid_rope(x, freqs_list)

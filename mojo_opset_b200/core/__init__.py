@@ -3,6 +3,7 @@
 
 from .backend_registry import MojoBackendRegistry
 from .operator import MojoOperator
+from .operators.activation import MojoGelu
 from .operators.activation import MojoSilu
 from .operators.activation import MojoSwiGLU
 from .operators.attention import MojoPagedDecodeGQA
@@ -13,14 +14,17 @@ from .operators.fused_attention_input import MojoNormRoPEStoreKV
 from .operators.fused_attention_input import MojoRoPEStoreKV
 from .operators.kv_cache import MojoStorePagedKVCache
 from .operators.kv_cache import build_paged_kv_chunk_metadata
+from .operators.normalization import MojoLayerNorm
 from .operators.normalization import MojoResidualAddRMSNorm
 from .operators.normalization import MojoRMSNorm
 from .operators.position_embedding import MojoApplyRoPE
+from .operators.position_embedding import MojoGridRoPE
 from .operators.position_embedding import MojoRotaryEmbedding
 
 __all__ = [
     "MojoBackendRegistry",
     "MojoOperator",
+    "MojoGelu",
     "MojoSilu",
     "MojoSwiGLU",
     "MojoPagedDecodeGQA",
@@ -31,8 +35,10 @@ __all__ = [
     "MojoRoPEStoreKV",
     "MojoStorePagedKVCache",
     "build_paged_kv_chunk_metadata",
+    "MojoLayerNorm",
     "MojoResidualAddRMSNorm",
     "MojoRMSNorm",
     "MojoApplyRoPE",
+    "MojoGridRoPE",
     "MojoRotaryEmbedding",
 ]

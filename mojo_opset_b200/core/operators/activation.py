@@ -5,6 +5,13 @@ import torch
 from ..operator import MojoOperator
 
 
+class MojoGelu(MojoOperator):
+    """Exact (erf) GELU element-wise, dtype preserved (reference ``activation.py:6-17``)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return MojoOperator.forward(self)
+
+
 class MojoSilu(MojoOperator):
     """``x * sigmoid(x)`` element-wise, dtype preserved."""
 

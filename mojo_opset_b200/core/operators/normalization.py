@@ -5,6 +5,30 @@ import torch
 from ..operator import MojoOperator
 
 
+class MojoLayerNorm(MojoOperator):
+    """``F.layer_norm`` over the last dim with an optional elementwise affine (reference
+    ``normalization.py:19-66``)."""
+
+    def __init__(self, norm_size: int, eps: float = 1e-5, elementwise_affine: bool = True, **kwargs):
+        super().__init__(**kwargs)
+        self.norm_size = norm_size
+        self.elementwise_affine = elementwise_affine
+        if elementwise_affine:
+            self.weight = torch.nn.Parameter(torch.empty(norm_size, **self.tensor_factory_kwargs))
+            self.bias = torch.nn.Parameter(torch.empty(norm_size, **self.tensor_factory_kwargs))
+        else:
+            self.weight = None
+            self.bias = None
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_state: torch.Tensor) -> torch.Tensor:
+        return MojoOperator.forward(self)
+
+    def extra_repr(self) -> str:
+        return (f"norm_size={self.norm_size!r}, variance_epsilon={self.variance_epsilon!r}, "
+                f"elementwise_affine={self.elementwise_affine!r}")
+
+
 class MojoRMSNorm(MojoOperator):
     """``y = x * rsqrt(mean(x^2) + eps) * weight`` over the last dim, fp32 math, one rounding."""
 

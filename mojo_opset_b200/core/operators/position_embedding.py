@@ -85,3 +85,12 @@ class MojoApplyRoPE(MojoOperator):
 
     def extra_repr(self) -> str:
         return f"interleaved={self.interleaved!r}"
+
+
+class MojoGridRoPE(MojoOperator):
+    """3-D grid RoPE of the DiT block (reference ``experimental/operators/position_embedding.py:80-118``):
+    ``x [B, L, N, D]`` as interleaved complex pairs times a per-sample complex phase table ``freqs_list[b]
+    [seq_len_b, 1, D/2]``; tokens past ``seq_len_b = F*H*W`` are passed through."""
+
+    def forward(self, x: torch.Tensor, grid_sizes: torch.Tensor, freqs_list) -> torch.Tensor:
+        return MojoOperator.forward(self)

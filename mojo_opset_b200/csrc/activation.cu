@@ -35,7 +35,15 @@ template <typename T> __device__ __forceinline__ void clamp_pair(float& gf, floa
   if (gf == gf) gf = round_through<T>(fminf(gf, limit));
 }
 
-template <typename T, bool GATED, bool CLAMP>
+// exact (erf) GELU, the default of torch.nn.functional.gelu: 0.5 * x * (1 + erf(x / sqrt(2))) in fp32
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <typename T, bool GELU> __device__ __forceinline__ float unary_f(float x) {
+  if constexpr (GELU) return gelu_f(x);
+  else return silu_f<T>(x);
+}
+
+template <typename T, bool GATED, bool CLAMP, bool GELU = false>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 8 : 4) act_kernel(const T* __restrict__ gate, const T* __restrict__ up,
                                                   T* __restrict__ out, int64_t rows, int64_t cols, int64_t g_rs,
                                                   int64_t u_rs, int64_t o_rs, float limit) {
@@ -60,7 +68,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 8 : 4) act_kernel(const 
           if (CLAMP) clamp_pair<T>(gf, uf, limit);
           ov.v[e] = DType<T>::from_f(__fmul_rn(round_through<T>(silu_f<T>(gf)), uf));
         } else {
-          ov.v[e] = DType<T>::from_f(silu_f<T>(gf));
+          ov.v[e] = DType<T>::from_f(unary_f<T, GELU>(gf));
         }
       }
       st_vec(o + v * N, ov);
@@ -74,14 +82,14 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 8 : 4) act_kernel(const 
         if (CLAMP) clamp_pair<T>(gf, uf, limit);
         o[c] = DType<T>::from_f(__fmul_rn(round_through<T>(silu_f<T>(gf)), uf));
       } else {
-        o[c] = DType<T>::from_f(silu_f<T>(gf));
+        o[c] = DType<T>::from_f(unary_f<T, GELU>(gf));
       }
     }
   }
 }
 
 // scalar variant for rows whose strides / base pointers are not 16-byte aligned
-template <typename T, bool GATED>
+template <typename T, bool GATED, bool GELU = false>
 __global__ void __launch_bounds__(256) act_scalar_kernel(const T* __restrict__ gate, const T* __restrict__ up,
                                                          T* __restrict__ out, int64_t rows, int64_t cols, int64_t g_rs,
                                                          int64_t u_rs, int64_t o_rs, float limit) {
@@ -93,14 +101,15 @@ __global__ void __launch_bounds__(256) act_scalar_kernel(const T* __restrict__ g
         if (limit > 0.f) clamp_pair<T>(gf, uf, limit);
         out[row * o_rs + c] = DType<T>::from_f(__fmul_rn(round_through<T>(silu_f<T>(gf)), uf));
       } else {
-        out[row * o_rs + c] = DType<T>::from_f(silu_f<T>(gf));
+        out[row * o_rs + c] = DType<T>::from_f(unary_f<T, GELU>(gf));
       }
     }
   }
 }
 
 static int act_entry(const void* gate, const void* up, void* out, int64_t rows, int64_t cols, int64_t g_rs,
-                     int64_t u_rs, int64_t o_rs, float limit, int dtype, void* stream, bool gated) {
+                     int64_t u_rs, int64_t o_rs, float limit, int dtype, void* stream, bool gated,
+                     bool gelu = false) {
   MOJO_REQUIRE(rows >= 0 && cols >= 0, MOJO_B200_EINVAL, "activation: bad sizes");
   if (rows == 0 || cols == 0) return 0;
   MOJO_REQUIRE(gate && out && (!gated || up), MOJO_B200_EINVAL, "activation: null tensor pointer");
@@ -121,9 +130,11 @@ static int act_entry(const void* gate, const void* up, void* out, int64_t rows, 
     if (vec_ok) {
       if (gated && limit > 0.f) act_kernel<T, true, true><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
       else if (gated) act_kernel<T, true, false><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
+      else if (gelu) act_kernel<T, false, false, true><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
       else act_kernel<T, false, false><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
     } else {
       if (gated) act_scalar_kernel<T, true><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
+      else if (gelu) act_scalar_kernel<T, false, true><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
       else act_scalar_kernel<T, false><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
     }
     return check_launch("act_kernel");
@@ -142,4 +153,9 @@ extern "C" int mojo_b200_swiglu(const void* gate, const void* up, void* out, int
 extern "C" int mojo_b200_silu(const void* x, void* out, int64_t rows, int64_t cols, int64_t x_row_stride,
                               int64_t out_row_stride, int dtype, void* stream) {
   return mojo::act_entry(x, nullptr, out, rows, cols, x_row_stride, 0, out_row_stride, 0.f, dtype, stream, false);
+}
+
+extern "C" int mojo_b200_gelu(const void* x, void* out, int64_t rows, int64_t cols, int64_t x_row_stride,
+                              int64_t out_row_stride, int dtype, void* stream) {
+  return mojo::act_entry(x, nullptr, out, rows, cols, x_row_stride, 0, out_row_stride, 0.f, dtype, stream, false, true);
 }

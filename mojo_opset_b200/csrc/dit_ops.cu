@@ -1,0 +1,223 @@
+// The non-GEMM ops around MojoSdpa in the DiT block (modeling/wan2_2/mojo_wan_model.py):
+//
+//   MojoLayerNorm  core/operators/normalization.py:19-66     F.layer_norm over the last dim, optional affine
+//   MojoGridRoPE   experimental/operators/position_embedding.py:80-118   3-D grid RoPE: interleaved (re, im) pairs of
+//                  x[b, :seq_len] times a per-sample complex phase table, padding tokens passed through
+//
+// Both are one HBM pass.  LayerNorm follows rmsnorm.cu's shape: a row is owned by a group of threads that keeps it in
+// registers (four 16-byte loads in flight per thread), two-pass moments from registers (mean, then the centred sum
+// of squares).  GridRoPE is a flat one-vector-per-thread streaming kernel (full occupancy).
+#include "common.cuh"
+
+namespace mojo {
+
+constexpr int kLnCta = 256;
+constexpr int kLnPacks = 4;
+
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) LnPack { T v[VEC]; };
+
+template <typename T, int VEC, int TPR>
+__global__ void __launch_bounds__(TPR > kLnCta ? TPR : kLnCta) layernorm_kernel(
+    const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b, T* __restrict__ y, int64_t rows,
+    int hidden, int64_t x_rs, int64_t y_rs, float eps) {
+  constexpr int RPC = TPR >= kLnCta ? 1 : kLnCta / TPR;
+  const int lane_in_row = threadIdx.x % TPR;
+  const int64_t row = (int64_t)blockIdx.x * RPC + threadIdx.x / TPR;
+  const bool active = row < rows;
+  const int vecs = hidden / VEC;
+  __shared__ float part[2][32];
+
+  auto group_sum = [&](float v, int which) -> float {
+    if constexpr (TPR <= 32) {
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    } else {
+      v = warp_sum(v);
+      if ((threadIdx.x & 31) == 0) part[which][threadIdx.x >> 5] = v;
+      __syncthreads();
+      constexpr int WPR = TPR / 32;
+      const int w0 = (threadIdx.x / TPR) * WPR;
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < WPR; ++i) t += part[which][w0 + i];
+      return t;
+    }
+  };
+
+  LnPack<T, VEC> keep[kLnPacks];
+  float s = 0.f;
+  if (active) {
+    const T* xr = x + row * x_rs;
+#pragma unroll
+    for (int i = 0; i < kLnPacks; ++i) {
+      const int v = lane_in_row + i * TPR;
+      if (v < vecs) {
+        keep[i] = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s += DType<T>::to_f(keep[i].v[e]);
+      }
+    }
+    for (int v = lane_in_row + kLnPacks * TPR; v < vecs; v += TPR) {  // rows wider than the register slice
+      const LnPack<T, VEC> a = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) s += DType<T>::to_f(a.v[e]);
+    }
+  }
+  const float mean = group_sum(s, 0) / (float)hidden;
+  float ss = 0.f;
+  if (active) {
+    const T* xr = x + row * x_rs;
+#pragma unroll
+    for (int i = 0; i < kLnPacks; ++i) {
+      const int v = lane_in_row + i * TPR;
+      if (v < vecs) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float d = DType<T>::to_f(keep[i].v[e]) - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+    }
+    for (int v = lane_in_row + kLnPacks * TPR; v < vecs; v += TPR) {
+      const LnPack<T, VEC> a = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float d = DType<T>::to_f(a.v[e]) - mean;
+        ss = fmaf(d, d, ss);
+      }
+    }
+  }
+  const float var = group_sum(ss, 1) / (float)hidden;
+  if (!active) return;
+  const float inv = __fdiv_rn(1.0f, __fsqrt_rn(var + eps));
+  T* yr = y + row * y_rs;
+  auto emit = [&](const LnPack<T, VEC>& a, int v) {
+    LnPack<T, VEC> o;
+    LnPack<T, VEC> g, h;
+    if (w) g = *reinterpret_cast<const LnPack<T, VEC>*>(w + (int64_t)v * VEC);
+    if (b) h = *reinterpret_cast<const LnPack<T, VEC>*>(b + (int64_t)v * VEC);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = (DType<T>::to_f(a.v[e]) - mean) * inv;
+      if (w) t *= DType<T>::to_f(g.v[e]);
+      if (b) t += DType<T>::to_f(h.v[e]);
+      o.v[e] = DType<T>::from_f(t);
+    }
+    *reinterpret_cast<LnPack<T, VEC>*>(yr + (int64_t)v * VEC) = o;
+  };
+#pragma unroll
+  for (int i = 0; i < kLnPacks; ++i) {
+    const int v = lane_in_row + i * TPR;
+    if (v < vecs) emit(keep[i], v);
+  }
+  for (int v = lane_in_row + kLnPacks * TPR; v < vecs; v += TPR)
+    emit(*reinterpret_cast<const LnPack<T, VEC>*>(x + row * x_rs + (int64_t)v * VEC), v);
+}
+
+template <typename T, int VEC>
+static int launch_layernorm(const void* x, const void* w, const void* b, void* y, int64_t rows, int hidden, int64_t x_rs,
+                            int64_t y_rs, float eps, cudaStream_t s) {
+  const int vecs = hidden / VEC;
+  int tpr = 4;
+  while (tpr < 1024 && vecs > tpr * kLnPacks) tpr *= 2;
+  auto ctas_for = [&](int t) { const int rpc = t >= kLnCta ? 1 : kLnCta / t; return (rows + rpc - 1) / rpc; };
+  while (tpr < 1024 && vecs >= tpr * 2 && ctas_for(tpr) < 2 * kNumSMs) tpr *= 2;
+#define LN_RUN(TPR)                                                                                           \
+  layernorm_kernel<T, VEC, TPR><<<(unsigned)ctas_for(TPR), (TPR > kLnCta ? TPR : kLnCta), 0, s>>>(            \
+      (const T*)x, (const T*)w, (const T*)b, (T*)y, rows, hidden, x_rs, y_rs, eps)
+  switch (tpr) {
+    case 4: LN_RUN(4); break;
+    case 8: LN_RUN(8); break;
+    case 16: LN_RUN(16); break;
+    case 32: LN_RUN(32); break;
+    case 64: LN_RUN(64); break;
+    case 128: LN_RUN(128); break;
+    case 256: LN_RUN(256); break;
+    case 512: LN_RUN(512); break;
+    default: LN_RUN(1024); break;
+  }
+#undef LN_RUN
+  return check_launch("layernorm_kernel");
+}
+
+// ---- grid RoPE: x [L, N, D] of one sample, phase [seq_len, D/2] complex64 as interleaved (cos, sin) fp32 ----------
+template <typename T, int VEC>  // VEC elements (= VEC/2 complex pairs) per thread
+__global__ void __launch_bounds__(256) grid_rope_kernel(const T* __restrict__ x, const float* __restrict__ phase,
+                                                        T* __restrict__ out, int64_t seq_len, int64_t tokens, int heads,
+                                                        int head_dim, int64_t x_st, int64_t x_sh, int64_t o_st,
+                                                        int64_t o_sh, int64_t phase_st) {
+  const int vecs_per_head = head_dim / VEC;
+  const int64_t total = tokens * heads * vecs_per_head;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs_per_head);
+    const int64_t th = i / vecs_per_head;
+    const int h = (int)(th % heads);
+    const int64_t t = th / heads;
+    LnPack<T, VEC> a = *reinterpret_cast<const LnPack<T, VEC>*>(x + t * x_st + (int64_t)h * x_sh + v * VEC);
+    if (t < seq_len) {
+      const float* ph = phase + t * phase_st + v * VEC;  // (cos, sin) of pair j at [2j, 2j+1]
+      float c[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) *reinterpret_cast<float4*>(c + e) = *reinterpret_cast<const float4*>(ph + e);
+#pragma unroll
+      for (int e = 0; e < VEC; e += 2) {
+        const float re = DType<T>::to_f(a.v[e]), im = DType<T>::to_f(a.v[e + 1]);
+        // complex product exactly as ATen evaluates it: (ac - bd) + i(ad + bc), each product rounded (no FMA)
+        a.v[e] = DType<T>::from_f(__fsub_rn(__fmul_rn(re, c[e]), __fmul_rn(im, c[e + 1])));
+        a.v[e + 1] = DType<T>::from_f(__fadd_rn(__fmul_rn(re, c[e + 1]), __fmul_rn(im, c[e])));
+      }
+    }
+    *reinterpret_cast<LnPack<T, VEC>*>(out + t * o_st + (int64_t)h * o_sh + v * VEC) = a;
+  }
+}
+
+}  // namespace mojo
+
+extern "C" int mojo_b200_layer_norm(const void* x, const void* weight, const void* bias, void* y, int64_t rows,
+                                    int hidden, int64_t x_row_stride, int64_t y_row_stride, float eps, int dtype,
+                                    void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(rows >= 0 && hidden > 0, MOJO_B200_EINVAL, "layer_norm: bad sizes");
+  if (rows == 0) return 0;
+  MOJO_REQUIRE(x && y, MOJO_B200_EINVAL, "layer_norm: null tensor pointer");
+  MOJO_REQUIRE(rows <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "layer_norm: too many rows");
+  const int eb = dtype_bytes(dtype);
+  const int full = 16 / eb;
+  uintptr_t bits = (uintptr_t)x | (uintptr_t)y | (uintptr_t)(x_row_stride * eb) | (uintptr_t)(y_row_stride * eb) |
+                   (uintptr_t)weight | (uintptr_t)bias;
+  const bool wide = hidden % full == 0 && (bits & 15) == 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    if (wide) return launch_layernorm<T, 16 / (int)sizeof(T)>(x, weight, bias, y, rows, hidden, x_row_stride, y_row_stride, eps, s);
+    return launch_layernorm<T, 1>(x, weight, bias, y, rows, hidden, x_row_stride, y_row_stride, eps, s);
+  });
+}
+
+extern "C" int mojo_b200_grid_rope(const void* x, const float* phase, void* out, int64_t seq_len, int64_t tokens,
+                                   int heads, int head_dim, int64_t x_stride_t, int64_t x_stride_h, int64_t o_stride_t,
+                                   int64_t o_stride_h, int64_t phase_stride_t, int dtype, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(tokens >= 0 && seq_len >= 0 && seq_len <= tokens && heads > 0 && head_dim > 0 && head_dim % 2 == 0,
+               MOJO_B200_EINVAL, "grid_rope: bad sizes");
+  if (tokens == 0) return 0;
+  MOJO_REQUIRE(x && out && (phase || seq_len == 0), MOJO_B200_EINVAL, "grid_rope: null tensor pointer");
+  const int eb = dtype_bytes(dtype);
+  const int full = 16 / eb;
+  const int64_t strides[] = {x_stride_t, x_stride_h, o_stride_t, o_stride_h};
+  bool wide = head_dim % full == 0 && aligned16(x) && aligned16(out) && aligned16(phase) && phase_stride_t % 4 == 0;
+  for (int64_t st : strides) wide = wide && st % full == 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  MOJO_REQUIRE(wide, MOJO_B200_EUNSUPPORTED, "grid_rope: head_dim, strides and pointers must allow 16-byte vectors");
+  const int64_t total = tokens * heads * (head_dim / full);
+  int64_t grid = (total + 255) / 256;
+  grid = grid < 1 ? 1 : (grid > 0x7fffffffLL ? 0x7fffffffLL : grid);
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    grid_rope_kernel<T, 16 / (int)sizeof(T)><<<(unsigned)grid, 256, 0, s>>>(
+        (const T*)x, phase, (T*)out, seq_len, tokens, heads, head_dim, x_stride_t, x_stride_h, o_stride_t, o_stride_h,
+        phase_stride_t);
+    return check_launch("grid_rope_kernel");
+  });
+}

@@ -128,6 +128,11 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __device__ __forceinline__ void st_flag_sys(uint32_t* flag, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
 }
+// several flags behind ONE system fence: fence + relaxed stores form the same release pattern as st.release per
+// flag, without paying a system-scope fence per destination rank
+__device__ __forceinline__ void st_flag_relaxed_sys(uint32_t* flag, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* flag) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
@@ -331,8 +336,9 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
             for (int d = 0; d < p.world; ++d) bulk_store(p.ws[d] + one_off(p, par, t, p.rank), image, kImageBytes);
             tma_store_commit();
             tma_store_wait_all();  // image read and the peer writes performed
+            __threadfence_system();
             for (int d = 0; d < p.world; ++d)
-              st_flag_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_one_off(p, par, t, p.rank)), epoch);
+              st_flag_relaxed_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_one_off(p, par, t, p.rank)), epoch);
           } else {
             const int owner = t % p.world, local_tile = t / p.world;
             bulk_store(p.ws[owner] + partial_off(p, par, local_tile, p.rank), image, kImageBytes);
@@ -436,8 +442,9 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
           for (int d = 0; d < p.world; ++d) bulk_store(p.ws[d] + dst, image, slab_bytes);
           tma_store_commit();
           tma_store_wait_all();
+          __threadfence_system();
           for (int d = 0; d < p.world; ++d)
-            st_flag_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_result_off(p, par, t, slab)), epoch);
+            st_flag_relaxed_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_result_off(p, par, t, slab)), epoch);
         }
         epi_barrier();  // image and red_in are free again
       }

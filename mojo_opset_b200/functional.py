@@ -520,3 +520,62 @@ def norm_rope_store_kv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: t
         _lib.dtype_id(q.dtype), _lib.dtype_id(cos.dtype), _lib.stream_ptr(dev))
     _lib.check(lib, rc, "norm_rope_store_kv")
     return (q_out, k_out) if want_k else q_out
+
+
+# ------------------------------------------------------------------------------------------------------
+# DiT block: MojoGelu / MojoLayerNorm / MojoGridRoPE
+# ------------------------------------------------------------------------------------------------------
+def gelu(x: torch.Tensor) -> torch.Tensor:
+    dev = _require_cuda(x)
+    lib = _lib.load()
+    out = torch.empty(x.shape, dtype=x.dtype, device=dev)
+    if x.numel() == 0:
+        return out
+    xr, rows, cols, x_rs = _rows_cols(x)
+    rc = lib.mojo_b200_gelu(xr.data_ptr(), out.data_ptr(), rows, cols, x_rs, cols, _lib.dtype_id(x.dtype),
+                            _lib.stream_ptr(dev))
+    _lib.check(lib, rc, "gelu")
+    return out
+
+
+def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    dev = _require_cuda(x, weight, bias)
+    lib = _lib.load()
+    hidden = x.shape[-1]
+    for name, t in (("weight", weight), ("bias", bias)):
+        if t is not None and (t.dtype != x.dtype or tuple(t.shape) != (hidden,)):
+            raise NotImplementedError(f"layer_norm: {name} must be [{hidden}] of dtype {x.dtype}")
+    xr = _as_rows(x)
+    y = torch.empty(x.shape, dtype=x.dtype, device=dev)
+    if x.numel() == 0:
+        return y
+    w = None if weight is None else weight.detach().contiguous()
+    b = None if bias is None else bias.detach().contiguous()
+    rc = lib.mojo_b200_layer_norm(xr.data_ptr(), _lib.ptr(w), _lib.ptr(b), y.data_ptr(), xr.shape[0], hidden,
+                                  xr.stride(0), hidden, float(eps), _lib.dtype_id(x.dtype), _lib.stream_ptr(dev))
+    _lib.check(lib, rc, "layer_norm")
+    return y
+
+
+def grid_rope(x: torch.Tensor, freqs_list) -> torch.Tensor:
+    """``x [B, L, N, D]`` (interleaved complex pairs); ``freqs_list[b]``: complex ``[seq_len_b, 1, D/2]``.  The sequence
+    length of a sample is the phase table's (no host read of ``grid_sizes``); one launch per sample."""
+    dev = _require_cuda(x, *freqs_list)
+    lib = _lib.load()
+    if x.dim() != 4 or x.shape[-1] % 2:
+        raise ValueError("grid_rope: x must be [B, L, N, D] with even D")
+    if len(freqs_list) != x.shape[0]:
+        raise ValueError("grid_rope: one phase table per sample expected")
+    x = _inner_contiguous(x)
+    batch, tokens, heads, d = x.shape
+    out = torch.empty((batch, tokens, heads, d), dtype=x.dtype, device=dev)
+    for i, fr in enumerate(freqs_list):
+        if not fr.is_complex() or fr.shape[-1] != d // 2 or fr.numel() != fr.shape[0] * (d // 2):
+            raise ValueError(f"grid_rope: freqs_list[{i}] must be complex [seq_len, 1, {d // 2}]")
+        ph = torch.view_as_real(fr.to(torch.complex64).reshape(fr.shape[0], d // 2).contiguous())
+        seq_len = min(fr.shape[0], tokens)
+        rc = lib.mojo_b200_grid_rope(x[i].data_ptr(), ph.data_ptr(), out[i].data_ptr(), seq_len, tokens, heads, d,
+                                     x.stride(1), x.stride(2), out.stride(1), out.stride(2), d,
+                                     _lib.dtype_id(x.dtype), _lib.stream_ptr(dev))
+        _lib.check(lib, rc, "grid_rope")
+    return out

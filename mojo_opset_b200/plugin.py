@@ -36,6 +36,9 @@ OPS = (
     "SwiGLU",
     "Silu",
     "GemmAllReduce",
+    "Gelu",
+    "LayerNorm",
+    "GridRoPE",
 )
 
 
@@ -62,6 +65,13 @@ def register(upstream=None) -> Dict[str, type]:
     created = {}
     for op in OPS:
         core_cls = getattr(upstream, "Mojo" + op, None)
+        if core_cls is None:  # ops the reference still keeps under mojo_opset.experimental (e.g. MojoGridRoPE)
+            try:
+                import importlib
+
+                core_cls = getattr(importlib.import_module(upstream.__name__ + ".experimental"), "Mojo" + op, None)
+            except ImportError:
+                core_cls = None
         our_cls = getattr(ours, "B200" + op, None)
         if core_cls is None or our_cls is None:
             continue

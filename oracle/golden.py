@@ -318,3 +318,29 @@ def norm_rope_store_kv(q, k, v, cos, sin, key_cache, value_cache, block_table, c
     plan = build_chunk_plan(block_table, cu_q_lens, context_kv_lens, key_cache.shape[2])
     store_paged_kv(k_rot, v, key_cache, value_cache, plan)
     return q_rot, k_rot
+
+
+# --------------------------------------------------------------------------------------------------
+# f3  DiT block ops: MojoGelu (activation.py:6-17), MojoLayerNorm (normalization.py:19-66),
+#     MojoGridRoPE (experimental/operators/position_embedding.py:80-118)
+# --------------------------------------------------------------------------------------------------
+def gelu(x):
+    return F.gelu(x)
+
+
+def layer_norm(x, weight, bias, eps: float):
+    return F.layer_norm(x, [x.shape[-1]], weight=weight, bias=bias, eps=eps)
+
+
+def grid_rope(x, grid_sizes, freqs_list):
+    """Per sample: the first F*H*W tokens as complex pairs (fp32) times the phase table, the rest unchanged; the
+    result is cast back to x's dtype (position_embedding.py:106-118)."""
+    n = x.size(2)
+    output = []
+    for i, (f, h, w) in enumerate(grid_sizes.tolist()):
+        seq_len = f * h * w
+        x_i = torch.view_as_complex(x[i, :seq_len].to(torch.float32).reshape(seq_len, n, -1, 2))
+        x_i = torch.view_as_real(x_i * freqs_list[i]).flatten(2)
+        x_i = torch.cat([x_i, x[i, seq_len:]])
+        output.append(x_i)
+    return torch.stack(output).type_as(x)

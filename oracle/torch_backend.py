@@ -124,3 +124,24 @@ class TorchNormRoPEStoreKV(core.MojoNormRoPEStoreKV):
     def forward(self, q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens, context_kv_lens):
         return golden.norm_rope_store_kv(q, k, v, cos, sin, key_cache, value_cache, block_table, cu_q_lens,
                                          context_kv_lens, self.q_weight, self.k_weight, self.variance_epsilon)[0]
+
+
+class TorchGelu(core.MojoGelu):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, x):
+        return golden.gelu(x)
+
+
+class TorchLayerNorm(core.MojoLayerNorm):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, hidden_state):
+        return golden.layer_norm(hidden_state, self.weight, self.bias, self.variance_epsilon)
+
+
+class TorchGridRoPE(core.MojoGridRoPE):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, x, grid_sizes, freqs_list):
+        return golden.grid_rope(x, grid_sizes, freqs_list)

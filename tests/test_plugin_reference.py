@@ -17,8 +17,9 @@ from mojo_opset_b200 import plugin
 made = plugin.register()
 assert sorted(made) == sorted(plugin.OPS), sorted(made)
 assert plugin.register() == {}                      # idempotent
+import mojo_opset.experimental as experimental       # MojoGridRoPE still lives there upstream
 for op in plugin.OPS:
-    core = getattr(mojo_opset, "Mojo" + op)
+    core = getattr(mojo_opset, "Mojo" + op, None) or getattr(experimental, "Mojo" + op)
     assert core.get_registered_backends()[:2] == ("b200", "torch"), (op, core.get_registered_backends())
     impl = core.get_backend_impl("b200", strict=True)
     assert impl.__name__ == "B200" + op and impl.__base__ is core           # direct subclass (TP wrapper lookup)
