@@ -263,6 +263,24 @@ MOJO_B200_API int mojo_b200_grid_rope(const void* x, const float* phase, void* o
                         int heads, int head_dim, int64_t x_stride_t, int64_t x_stride_h,
                         int64_t o_stride_t, int64_t o_stride_h, int64_t phase_stride_t, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Paged-KV bookkeeping on the device: PagedAttentionRuntimeState._reserve / _allocate_blocks /
+ * _build_positions (mojo_opset/runtime/runtime.py:112-158) without the per-sequence .item() host syncs.
+ *
+ * paged_reserve: for every sequence b (batch order) append q_lens[b] tokens (NULL = 1 each): new logical blocks
+ * take the top entries of the free stack free_blocks[0 .. *num_free) exactly in the reference's order, are written
+ * to block_tables[b, old_blocks ...], *num_free shrinks, total_seq_lens[b] += q_lens[b], and
+ * context_lens_out[b] receives the length BEFORE the append.  If the request cannot be served nothing changes
+ * and *error_flag is set (1 = out of blocks, 2 = a sequence would exceed max_blocks_per_seq).
+ * paged_positions: positions[t] = context_lens[seq(t)] + (t - cu_q_lens[seq(t)]) for prefill tokens.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_paged_reserve(int32_t* block_tables, int64_t table_stride, int max_blocks_per_seq,
+                            int32_t* total_seq_lens, const int32_t* q_lens, const int32_t* free_blocks,
+                            int32_t* num_free, int32_t* context_lens_out, int batch, int block_size,
+                            int32_t* error_flag, void* stream);
+MOJO_B200_API int mojo_b200_paged_positions(int64_t* positions, const int32_t* cu_q_lens, const int32_t* context_lens,
+                              int batch, int64_t num_tokens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ SIGNATURES = {
     "mojo_b200_gelu": (I, [P, P, L, L, L, L, I, P]),
     "mojo_b200_layer_norm": (I, [P, P, P, P, L, I, L, L, F, I, P]),
     "mojo_b200_grid_rope": (I, [P, P, P, L, L, I, I, L, L, L, L, L, I, P]),
+    "mojo_b200_paged_reserve": (I, [P, L, I, P, P, P, P, P, I, I, P, P]),
+    "mojo_b200_paged_positions": (I, [P, P, P, I, L, P]),
     "mojo_b200_symm_alloc": (I, [Z, ctypes.POINTER(c_void_p)]),
     "mojo_b200_symm_free": (I, [P]),
     "mojo_b200_symm_export": (I, [P, P]),
