@@ -131,6 +131,20 @@ def bench_elementwise(rows_list):
         us = time_us([lambda s=s: F.store_paged_kv(s[0], s[1], s[2], s[3], chunk_metadata=s[4]) for s in sets])
         out.append(("store_paged_kv", f"T={T} chunks={chunks}", nbytes, us))
         del sets
+        # DiT block ops: LayerNorm (2 streams + affine), exact GELU (2 streams)
+        nbytes = 2 * T * H * 2 + 2 * H * 2
+        n = copies_for(nbytes)
+        sets = [rnd(T, H) for _ in range(n)]
+        lw, lb = rnd(H), rnd(H)
+        us = time_us([lambda s=s: F.layer_norm(s, lw, lb, 1e-6) for s in sets])
+        out.append(("layer_norm", f"{T}x{H}", nbytes, us))
+        del sets
+        nbytes = 2 * T * I * 2
+        n = copies_for(nbytes)
+        sets = [rnd(T, I) for _ in range(n)]
+        us = time_us([lambda s=s: F.gelu(s) for s in sets])
+        out.append(("gelu", f"{T}x{I}", nbytes, us))
+        del sets
         # fused q/k-norm + RoPE + KV store (one pass): reads q, k, v, writes q' and the k', v slots
         nbytes = (2 * Hq + 4 * Hkv) * D * 2 * T + 2 * T * D * 4 + 2 * D * 2
         n = copies_for(nbytes)

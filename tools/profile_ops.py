@@ -23,7 +23,14 @@ table = torch.randperm(nb)[: T // bs].view(1, -1).to(torch.int32).to(DEV)
 cu = torch.tensor([0, T], dtype=torch.int32, device=DEV)
 ctx = torch.zeros(1, dtype=torch.int32, device=DEV)
 wd = rnd(D)
+lw, lb = rnd(H), rnd(H)
+gx = rnd(256, 4096)
+gw = rnd(8192, 4096)
 for _ in range(2):
+    F.norm_rope_store_kv(q, k, k, cos, sin, kc, vc, table, cu, ctx, wd, wd, 1e-6)
+    F.layer_norm(x, lw, lb, 1e-6)
+    F.gelu(g)
+    F.gemm_allreduce(gx, gw, None, None)
     F.residual_add_rms_norm(x, r, w, 1e-6)
     F.rms_norm(x, w, 1e-6)
     F.rms_norm(q, wd, 1e-6)
