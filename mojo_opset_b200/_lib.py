@@ -18,7 +18,8 @@ from ctypes import c_void_p
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libmojo_b200.so")
+# MOJO_B200_LIB: developer override (A/B builds of the same ABI, tools/build_variant.sh); the default is the in-tree build
+LIB_PATH = os.environ.get("MOJO_B200_LIB") or os.path.join(_PKG_DIR, "libmojo_b200.so")
 
 EINVAL, EUNSUPPORTED, EWORKSPACE = -1, -2, -3
 BF16, F16, F32 = 0, 1, 2

@@ -146,3 +146,32 @@ def test_contracts_raise_like_reference():
         B200ApplyRoPE()(q, q[None], torch.randn(2, 64), torch.randn(2, 64))
     with pytest.raises(AssertionError):
         B200ApplyRoPE(interleaved=True)
+
+
+def test_qwen3_patch_swaps_and_reverts():
+    """``apply_mojo_to_qwen3`` (reference utils/patching.py:4-59) replaces HF's rotary fn / RMSNorm / MLP classes
+    statically and ``revert_mojo_from_qwen3`` restores them; no compute."""
+    pytest.importorskip("transformers")
+    from transformers.models.qwen3 import modeling_qwen3
+
+    import mojo_opset_b200 as m
+    from mojo_opset_b200.utils.patching import apply_mojo_to_qwen3
+    from mojo_opset_b200.utils.patching import revert_mojo_from_qwen3
+
+    orig = (modeling_qwen3.apply_rotary_pos_emb, modeling_qwen3.Qwen3RMSNorm, modeling_qwen3.Qwen3MLP)
+    with pytest.raises(AssertionError):
+        apply_mojo_to_qwen3(cross_entropy=True, fused_linear_cross_entropy=True)
+    old = os.environ.get("MOJO_BACKEND")
+    try:
+        if not torch.cuda.is_available():
+            os.environ.pop("MOJO_BACKEND", None)  # no b200 registration on a CPU box: the core op is the interface
+        apply_mojo_to_qwen3()
+        assert isinstance(modeling_qwen3.apply_rotary_pos_emb, m.MojoApplyRoPE)
+        assert modeling_qwen3.Qwen3RMSNorm is m.MojoRMSNorm
+        assert modeling_qwen3.Qwen3MLP.__name__ == "MojoSwiGLUMLP"
+        apply_mojo_to_qwen3(rope=False, rms_norm=False, swiglu=False)  # a no-op keeps the first originals
+    finally:
+        revert_mojo_from_qwen3()
+        if old is not None:
+            os.environ["MOJO_BACKEND"] = old
+    assert (modeling_qwen3.apply_rotary_pos_emb, modeling_qwen3.Qwen3RMSNorm, modeling_qwen3.Qwen3MLP) == orig
