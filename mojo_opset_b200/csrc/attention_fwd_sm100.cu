@@ -20,6 +20,16 @@
 //                over S in TMEM (tcgen05.st) -> arrive.  Epilogue: O row / l -> out.
 //   warp 10      TMEM allocation (all 512 columns: S0 S1 O0 O1, P_t aliases the first 64 columns of S_t).
 //
+// PAIR = true: the same kernel on a 2-CTA cluster with cta_group::2 MMAs (M = 256: the two CTAs' query tiles in one
+// instruction).  The two CTAs work on two query heads of one KV group (GQA, even group) or on two adjacent query
+// blocks of one head (non-causal), so they need the SAME K/V tiles and each stages only half of every tile: CTA r
+// holds keys [64 r, 64 r + 64) of a K tile (the N split of S = Q K^T) and value columns [64 r, 64 r + 64) of a V
+// tile (the N split of O = P V).  Per CTA the shared-memory operand traffic of a QK MMA drops from 8 KB to 6 KB
+// (below the 128 B/clk the SS form is limited by), of a PV MMA from 4 KB to 2 KB, and L2 -> SM traffic halves.
+// The leader CTA issues every MMA; TMA completion of the peer's halves reaches it through a relay (the peer's
+// otherwise idle MMA warp: wait local barrier -> remote arrive); the peer's softmax warps arrive remotely on the
+// leader's P barrier; commits multicast to both CTAs.
+//
 // FLOPs = 4 * D * (unmasked (q, k) pairs) per query head; the roofline is the bf16 tensor peak.
 #include <cmath>
 #include <cstdlib>
@@ -39,11 +49,12 @@ constexpr int kBN = 128;                      // keys per KV tile
 constexpr int kD = 128;
 constexpr int kHalfBytes = 128 * 128;         // 128 lines of 128 B: one 64-column half of a tile
 constexpr int kTileBytes = 2 * kHalfBytes;    // 32 KB
-constexpr int kStages = 4;                    // K/V ring
+constexpr int kRingBytes = 4 * kTileBytes;    // K/V ring: 4 stages of a tile, or (PAIR) 8 stages of half a tile
 constexpr int kTmemCols = 512;
 constexpr int kLoadWarp = 8, kMmaWarp = 9, kAllocWarp = 10;
 constexpr float kRescaleThreshold = 8.f;      // log2 units
-constexpr size_t kSmemBytes = 1024 + (2 + kStages) * (size_t)kTileBytes + 256;
+constexpr int kPairDefault = 0;               // CTA pairs off until measured faster (MOJO_B200_ATTN_PAIR=1)
+constexpr size_t kSmemBytes = 1024 + 2 * (size_t)kTileBytes + kRingBytes + 512;
 
 struct Params {
   void* out;
@@ -52,9 +63,10 @@ struct Params {
   const int32_t* tables;
   int64_t table_stride;
   int64_t o_sb, o_st, o_sh;
-  int max_blocks, block_size, log2_bs, box_rows;
+  int max_blocks, block_size, log2_bs, box_rows, box_rows_v;
   int num_q_heads, num_kv_heads, group, interleave, dense;
   int batch, m_blocks;
+  int pair_heads;  // PAIR: the two CTAs take two heads of one KV group (else two adjacent query blocks)
   int q_len_dense, kv_len_dense;
   float scale_log2;
   long long* trace;  // developer timeline (MOJO_ATTN_TRACE builds only, tools/attn_trace.py)
@@ -70,10 +82,7 @@ struct Params {
 #define TRACE(role, j, ev) do {} while (0)
 #endif
 
-__device__ __forceinline__ uint32_t ring_stage(uint32_t c) { return c % kStages; }
-__device__ __forceinline__ uint32_t ring_parity(uint32_t c) { return (c / kStages) & 1u; }
-
-template <typename T, bool CAUSAL, bool ROUND_S, int EMU>
+template <typename T, bool CAUSAL, bool ROUND_S, int EMU, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map,
                       const __grid_constant__ CUtensorMap v_map, const Params p) {
@@ -81,23 +90,54 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + 2 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * kTileBytes);
+  constexpr int kStages = PAIR ? 8 : 4;
+  constexpr int kStageBytes = kRingBytes / kStages;
+  auto ring_stage = [](uint32_t c) { return c % (uint32_t)kStages; };
+  auto ring_parity = [](uint32_t c) { return (c / (uint32_t)kStages) & 1u; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kRingBytes);
   uint64_t* q_full = bars;                  // [2]
   uint64_t* kv_full = bars + 2;             // [kStages]
   uint64_t* kv_empty = kv_full + kStages;   // [kStages]
   uint64_t* s_full = kv_empty + kStages;    // [2]  MMA -> softmax: S_t ready
   uint64_t* p_full = s_full + 2;            // [2]  softmax -> MMA: P_t written (and S_t consumed)
   uint64_t* o_full = p_full + 2;            // [2]  MMA -> softmax: last PV_t done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* peer_q_full = o_full + 2;       // [2]        PAIR, leader: the peer's Q tile landed (relay)
+  uint64_t* peer_kv_full = peer_q_full + 2; // [kStages]  PAIR, leader: the peer's half of a K/V tile landed (relay)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_kv_full + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   // 1-D grid in longest-processing-time order: CTAs are scheduled in linear order, so the query blocks with the most
   // keys (causal: the last ones) of EVERY (head, sequence) go first and the short ones fill the tail; heads vary
   // fastest so the q heads of one KV group run together and share K/V tiles in L2.
-  const int hq = (int)(blockIdx.x % (unsigned)p.num_q_heads);
-  const int rest = (int)(blockIdx.x / (unsigned)p.num_q_heads);
-  const int b = rest % p.batch;
-  const int m_blk = p.m_blocks - 1 - rest / p.batch;
+  int hq, b, m_blk, m_blk_lead;
+  if (PAIR) {
+    const unsigned cid = blockIdx.x >> 1;
+    if (p.pair_heads) {  // two heads of one KV group, same query block
+      const unsigned units = (unsigned)p.num_q_heads >> 1;
+      const int hp = (int)(cid % units);
+      const int rest = (int)(cid / units);
+      if (p.interleave) {  // ABAB: kv = h % Hkv, the group members are Hkv apart
+        const int kv = hp % p.num_kv_heads, gp = hp / p.num_kv_heads;
+        hq = (2 * gp + (int)rank) * p.num_kv_heads + kv;
+      } else {
+        hq = 2 * hp + (int)rank;
+      }
+      b = rest % p.batch;
+      m_blk = m_blk_lead = p.m_blocks - 1 - rest / p.batch;
+    } else {  // one head, two adjacent query blocks (non-causal only: both walk the same keys)
+      hq = (int)(cid % (unsigned)p.num_q_heads);
+      const int rest = (int)(cid / (unsigned)p.num_q_heads);
+      b = rest % p.batch;
+      m_blk_lead = 2 * (p.m_blocks - 1 - rest / p.batch);
+      m_blk = m_blk_lead + (int)rank;
+    }
+  } else {
+    hq = (int)(blockIdx.x % (unsigned)p.num_q_heads);
+    const int rest = (int)(blockIdx.x / (unsigned)p.num_q_heads);
+    b = rest % p.batch;
+    m_blk = m_blk_lead = p.m_blocks - 1 - rest / p.batch;
+  }
 
   int64_t q_start;
   int q_len, kv_len;
@@ -111,12 +151,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
     kv_len = p.cu_kv ? p.cu_kv[b + 1] - p.cu_kv[b] : q_len;
   }
   const int m0 = m_blk * 2 * kBM;
-  if (m0 >= q_len || kv_len <= 0) return;
+  // everything that decides participation is computed from the LEADER's rows, so both CTAs of a pair agree (a peer
+  // whose own rows are past the end still stages its operand halves and computes on rows nobody stores)
+  const int m0_lead = m_blk_lead * 2 * kBM;
+  if (m0_lead >= q_len || kv_len <= 0) return;
   const int off = kv_len - q_len;  // query row t sees keys 0 .. off + t
   int n_t[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int first = m0 + t * kBM;
+    const int first = m0_lead + t * kBM;
     int n = 0;
     if (first < q_len) {
       const int last = min(first + kBM, q_len) - 1;
@@ -133,18 +176,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1);
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[t], PAIR ? 8 : 4);  // one arrive per softmax warp (of both CTAs)
       mbar_init(&o_full[t], 1);
+      mbar_init(&peer_q_full[t], 1);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      mbar_init(&peer_kv_full[s], 1);
     }
     mbar_fence_init();
   }
-  if (warp == kAllocWarp) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kAllocWarp) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -167,25 +215,30 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         }
       }
       const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
-      const int box_rows = p.box_rows;
-      const int boxes_per_tile = kBN / box_rows;
-      const uint32_t box_bytes = (uint32_t)box_rows * 128u;  // one half of one box
       uint32_t c = 0;
       for (int j = 0; j < n_max; ++j) {
-        const int tok0 = j * kBN;
-        const int want = p.dense ? 1 : min(boxes_per_tile, (kv_len - tok0 + box_rows - 1) / box_rows);
 #pragma unroll 1
         for (int is_v = 0; is_v < 2; ++is_v, ++c) {
+          // what this CTA stages of the tile: everything, or (PAIR) keys [64 rank, +64) of K as [half][64][128 B] /
+          // value columns [64 rank, +64) of V as [128][128 B]
+          const int box_rows = is_v ? p.box_rows_v : p.box_rows;
+          const int rows = (PAIR && !is_v) ? kBN / 2 : kBN;       // key rows this CTA stages
+          const int tok0 = j * kBN + ((PAIR && !is_v) ? (int)rank * (kBN / 2) : 0);
+          const int halves = (PAIR && is_v) ? 1 : 2;              // 64-column halves this CTA stages
+          const uint32_t half_bytes = (uint32_t)rows * 128u;
+          const uint32_t box_bytes = (uint32_t)box_rows * 128u;   // one half of one box
+          const int want = p.dense ? 1 : max(0, min(rows / box_rows, (kv_len - tok0 + box_rows - 1) / box_rows));
           const uint32_t stage = ring_stage(c);
-          uint8_t* dst = sKV + stage * kTileBytes;
+          uint8_t* dst = sKV + stage * kStageBytes;
           if (lane == 0) {
             mbar_wait_bounded(&kv_empty[stage], ring_parity(c) ^ 1u);
-            mbar_expect_tx(&kv_full[stage], 2u * box_bytes * (uint32_t)want);
+            mbar_expect_tx(&kv_full[stage], (uint32_t)halves * box_bytes * (uint32_t)want);
           }
           __syncwarp();
           const CUtensorMap* map = is_v ? &v_map : &k_map;
-          for (int idx = lane; idx < 2 * want; idx += 32) {
-            const int box = idx >> 1, half = idx & 1;
+          for (int idx = lane; idx < halves * want; idx += 32) {
+            const int box = halves == 2 ? idx >> 1 : idx;
+            const int half = halves == 2 ? (idx & 1) : (int)rank;
             int blk, row;
             if (p.dense) {
               blk = b;
@@ -196,78 +249,115 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
               row = tok & (p.block_size - 1);
               blk = page < p.max_blocks ? table[page] : -1;  // out-of-range ids are zero-filled by the TMA unit
             }
-            tma_load_5d(dst + half * kHalfBytes + box * box_bytes, map, &kv_full[stage], 0, row, half, kvh, blk);
+            tma_load_5d(dst + (halves == 2 ? half : 0) * half_bytes + box * box_bytes, map, &kv_full[stage], 0, row,
+                        half, kvh, blk);
           }
         }
+      }
+    } else if (warp == kMmaWarp && PAIR && rank != 0) {
+      // ---------------------------------------------------------------------------- peer relay: "my halves landed"
+      // in the order the leader's MMA warp waits for them
+      if (lane == 0) {
+        const uint32_t pq = mapa_u32(smem_u32(peer_q_full), 0), pkv = mapa_u32(smem_u32(peer_kv_full), 0);
+        auto relay_kv = [&](uint32_t c) {
+          mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));
+          mbar_arrive_cluster(pkv + ring_stage(c) * 8u);
+        };
+        relay_kv(0);
+        for (int t = 0; t < 2; ++t) {
+          if (n_t[t] > 0) {
+            mbar_wait_bounded(&q_full[t], 0);
+            mbar_arrive_cluster(pq + (uint32_t)t * 8u);
+          }
+        }
+        for (uint32_t c = 1; c < 2u * (uint32_t)n_max; ++c) relay_kv(c);
       }
     } else if (warp == kMmaWarp) {
       // ---------------------------------------------------------------------------- MMA issuer (whole warp, converged)
       constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-      constexpr uint32_t idesc_qk = umma_idesc_f16(kFmt, kBM, kBN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(kFmt, kBM, kD, 0, 1);
+      constexpr int kM = PAIR ? 2 * kBM : kBM;  // PAIR: rows of both CTAs in one instruction
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kFmt, kM, kBN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kFmt, kM, kD, 0, 1);
+      // K-major K operand: [64-column half][rows][128 B]; PAIR stages 64 of the 128 key rows per CTA
+      constexpr uint32_t kKHalfStride = PAIR ? kHalfBytes / 2 : kHalfBytes;
       const uint32_t sQ_a = smem_u32(sQ), sKV_a = smem_u32(sKV);
+      auto mma_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if (PAIR) umma_ss_pair(d, ad, bd, idesc, acc); else umma_ss(d, ad, bd, idesc, acc);
+      };
+      auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if (PAIR) umma_ts_pair(d, a, bd, idesc, acc); else umma_ts(d, a, bd, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+      };
+      auto wait_kv = [&](uint32_t c) {  // this CTA's (and the peer's) part of ring item c has landed
+        mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));
+        if (PAIR) mbar_wait_bounded_cluster(&peer_kv_full[ring_stage(c)], ring_parity(c));
+      };
       auto qk = [&](int t, uint32_t k_stage) {  // S_t = Q_t K^T
-        const uint32_t qa = sQ_a + t * kTileBytes, ka = sKV_a + k_stage * kTileBytes;
+        const uint32_t qa = sQ_a + t * kTileBytes, ka = sKV_a + k_stage * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < kD / 16; ++ks) {
-          const uint32_t o = (uint32_t)(ks >> 2) * kHalfBytes + (uint32_t)(ks & 3) * 32u;
-          umma_ss(tmem + t * kBN, umma_desc_sw128(qa + o, 16, 1024), umma_desc_sw128(ka + o, 16, 1024), idesc_qk,
-                  ks > 0);
+          const uint32_t oq = (uint32_t)(ks >> 2) * kHalfBytes + (uint32_t)(ks & 3) * 32u;
+          const uint32_t ok = (uint32_t)(ks >> 2) * kKHalfStride + (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + t * kBN, umma_desc_sw128(qa + oq, 16, 1024), umma_desc_sw128(ka + ok, 16, 1024), idesc_qk,
+                 ks > 0);
         }
       };
       auto pv = [&](int t, uint32_t v_stage, bool acc) {  // O_t (+)= P_t V
-        const uint32_t va = sKV_a + v_stage * kTileBytes;
+        const uint32_t va = sKV_a + v_stage * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ++ks)
-          umma_ts(tmem + 2 * kBN + t * kD, tmem + t * kBN + ks * 8, umma_desc_sw128(va + ks * 2048u, kHalfBytes, 1024),
-                  idesc_pv, acc || ks > 0);
+          mma_ts(tmem + 2 * kBN + t * kD, tmem + t * kBN + ks * 8, umma_desc_sw128(va + ks * 2048u, kHalfBytes, 1024),
+                 idesc_pv, acc || ks > 0);
       };
       uint32_t c = 0;
-      mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));  // K(0)
+      wait_kv(c);  // K(0)
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (n_t[t] > 0) {
           mbar_wait_bounded(&q_full[t], 0);
+          if (PAIR) mbar_wait_bounded_cluster(&peer_q_full[t], 0);
           tc_fence_after();
           qk(t, ring_stage(c));
-          umma_commit(&s_full[t]);
+          commit(&s_full[t]);
         }
       }
-      umma_commit(&kv_empty[ring_stage(c)]);
+      commit(&kv_empty[ring_stage(c)]);
       ++c;
       for (int j = 0; j < n_max; ++j, c += 2) {
         const uint32_t cv = c, ck = c + 1;
         const bool more = j + 1 < n_max;
-        mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));  // V(j)
+        wait_kv(cv);  // V(j)
         if (j < n_t[0]) {
-          mbar_wait_bounded(&p_full[0], (uint32_t)j & 1u);
+          if (PAIR) mbar_wait_bounded_cluster(&p_full[0], (uint32_t)j & 1u); else mbar_wait_bounded(&p_full[0], (uint32_t)j & 1u);
           TRACE(2, j, 0);
           tc_fence_after();
           pv(0, ring_stage(cv), j > 0);
-          if (j == n_t[0] - 1) umma_commit(&o_full[0]);
+          if (j == n_t[0] - 1) commit(&o_full[0]);
         }
         if (more) {
-          mbar_wait_bounded(&kv_full[ring_stage(ck)], ring_parity(ck));  // K(j+1)
+          wait_kv(ck);  // K(j+1)
           tc_fence_after();
         }
         if (j + 1 < n_t[0]) {
           qk(0, ring_stage(ck));
-          umma_commit(&s_full[0]);
+          commit(&s_full[0]);
         }
         TRACE(2, j, 1);
         if (j < n_t[1]) {
-          mbar_wait_bounded(&p_full[1], (uint32_t)j & 1u);
+          if (PAIR) mbar_wait_bounded_cluster(&p_full[1], (uint32_t)j & 1u); else mbar_wait_bounded(&p_full[1], (uint32_t)j & 1u);
           TRACE(2, j, 2);
           tc_fence_after();
           pv(1, ring_stage(cv), j > 0);
-          if (j == n_t[1] - 1) umma_commit(&o_full[1]);
+          if (j == n_t[1] - 1) commit(&o_full[1]);
         }
-        umma_commit(&kv_empty[ring_stage(cv)]);
+        commit(&kv_empty[ring_stage(cv)]);
         if (j + 1 < n_t[1]) {
           qk(1, ring_stage(ck));
-          umma_commit(&s_full[1]);
+          commit(&s_full[1]);
         }
-        if (more) umma_commit(&kv_empty[ring_stage(ck)]);
+        if (more) commit(&kv_empty[ring_stage(ck)]);
         TRACE(2, j, 3);
       }
     }
@@ -383,18 +473,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           // P is exactly 0 there but 0 * NaN would poison O, so zero them (both warpgroups may, all store 0)
           const uint32_t cv = 2u * (uint32_t)j + 1u;
           mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));
-          uint8_t* sv = sKV + ring_stage(cv) * kTileBytes;
+          uint8_t* sv = sKV + ring_stage(cv) * kStageBytes;
           const int tid = threadIdx.x & 127;
-          for (int idx = tid; idx < (kBN - valid) * 16; idx += 128) {
-            const int r = valid + (idx >> 4), h = (idx >> 3) & 1, ch = idx & 7;
+          constexpr int kChunks = PAIR ? 8 : 16;  // 16-byte chunks per key row staged by this CTA (one / two halves)
+          for (int idx = tid; idx < (kBN - valid) * kChunks; idx += 128) {
+            const int r = valid + idx / kChunks, h = PAIR ? 0 : (idx >> 3) & 1, ch = idx & 7;
             *reinterpret_cast<uint4*>(sv + h * kHalfBytes + r * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
           }
           fence_async_smem();
+          if (PAIR) fence_acq_rel_cluster();  // the zeroed rows are read by both SMs' tensor cores (rare path)
         }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&p_full[t]), 0)); else mbar_arrive(&p_full[t]);
+        }
         if ((warp & 3) == 0) TRACE(t, j, 4);
       }
 
@@ -426,9 +520,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM until here
   if (warp == kAllocWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem, kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem, kTmemCols); else tmem_dealloc(tmem, kTmemCols);
   }
 }
 
@@ -463,13 +558,26 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
     return kAttnNotEligible;
   }
 
+  // CTA pairs (cta_group::2): two heads of one KV group when the group is even, else (non-causal only) two adjacent
+  // query blocks of one head.  MOJO_B200_ATTN_PAIR=0/1 overrides the default.
+  const int group = a.num_q_heads / a.num_kv_heads;
+  const bool pair_heads = group % 2 == 0;
+  const bool pair_ok = pair_heads || !a.causal;
+  const bool pair = pair_ok && env_int("MOJO_B200_ATTN_PAIR", kPairDefault) != 0;
+  int box_rows_v = box_rows;
+  if (pair) {  // a CTA stages 64 key rows of a K tile and all 128 key rows of one 64-column half of a V tile
+    const int64_t bs = a.rows_per_block;
+    box_rows = a.dense ? kBN / 2 : (bs < kBN / 2 ? (int)bs : kBN / 2);
+    box_rows_v = a.dense ? kBN : (bs < kBN ? (int)bs : kBN);
+  }
+
   CUtensorMap q_map, k_map, v_map;
   const int64_t q_sb = a.dense ? a.q_sb : a.q_rows * a.q_st;  // paged: a single "batch" (any valid stride)
   int rc = build_tile_map(a.q, a.dtype, a.q_rows, a.num_q_heads, a.dense ? a.batch : 1, q_sb, a.q_sh, a.q_st, kBM, &q_map);
   if (rc != 0) return forced ? rc : kAttnNotEligible;
   rc = build_tile_map(a.k, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.k_b, a.k_h, a.k_t, box_rows, &k_map);
   if (rc != 0) return forced ? rc : kAttnNotEligible;
-  rc = build_tile_map(a.v, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.v_b, a.v_h, a.v_t, box_rows, &v_map);
+  rc = build_tile_map(a.v, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.v_b, a.v_h, a.v_t, box_rows_v, &v_map);
   if (rc != 0) return forced ? rc : kAttnNotEligible;
 
   Params p;
@@ -477,7 +585,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.out = a.out;
   p.cu_q = a.cu_q; p.cu_kv = a.cu_kv; p.tables = a.tables; p.table_stride = a.table_stride;
   p.o_sb = a.dense ? a.o_sb : 0; p.o_st = a.o_st; p.o_sh = a.o_sh;
-  p.max_blocks = a.max_blocks; p.block_size = (int)a.rows_per_block; p.box_rows = box_rows;
+  p.max_blocks = a.max_blocks; p.block_size = (int)a.rows_per_block; p.box_rows = box_rows; p.box_rows_v = box_rows_v;
   while (!a.dense && (1 << p.log2_bs) < p.block_size) ++p.log2_bs;
   p.num_kv_heads = a.num_kv_heads; p.group = a.num_q_heads / a.num_kv_heads; p.interleave = a.interleave;
   p.dense = a.dense; p.q_len_dense = (int)a.q_len_dense; p.kv_len_dense = (int)a.kv_len_dense;
@@ -487,15 +595,32 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
 #endif
 
   p.num_q_heads = a.num_q_heads; p.batch = a.batch;
-  p.m_blocks = (int)((a.max_q_len + 2 * kBM - 1) / (2 * kBM));
-  const int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch;
+  // m_blocks counts the grid's steps along the query rows: 256 rows per CTA; a pair of query blocks covers 512
+  p.pair_heads = pair_heads ? 1 : 0;
+  const int64_t rows_per_step = (pair && !pair_heads) ? 4 * kBM : 2 * kBM;
+  p.m_blocks = (int)((a.max_q_len + rows_per_step - 1) / rows_per_step);
+  const int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch * ((pair && !pair_heads) ? 2 : 1);
   MOJO_REQUIRE(num_ctas <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "attention: grid too large");
-  dim3 grid((unsigned)num_ctas, 1, 1);
-#define LAUNCH_SM100(TT, PP, RR, EE)                                                                             \
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)num_ctas, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pair ? 1 : 0;
+#define LAUNCH_SM100_P(TT, PP, RR, EE, PAIR_)                                                                 \
   do {                                                                                                        \
-    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, EE>;                                                        \
+    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, EE, PAIR_>;                                                 \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));   \
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(q_map, k_map, v_map, p);                                     \
+    MOJO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, q_map, k_map, v_map, p));                                      \
+  } while (0)
+#define LAUNCH_SM100(TT, PP, RR, EE)                                                                          \
+  do {                                                                                                        \
+    if (pair) LAUNCH_SM100_P(TT, PP, RR, EE, true); else LAUNCH_SM100_P(TT, PP, RR, EE, false);               \
   } while (0)
 #define LAUNCH_SM100_EMU(TT, PP)                                                \
   do {                                                                          \
@@ -514,6 +639,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   else          { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, false); else LAUNCH_SM100_EMU(__half, false); }
 #undef LAUNCH_SM100_EMU
 #undef LAUNCH_SM100
+#undef LAUNCH_SM100_P
   return check_launch("attn_fwd_sm100_kernel");
 }
 
