@@ -53,7 +53,6 @@ constexpr int kRingBytes = 4 * kTileBytes;    // K/V ring: 4 stages of a tile, o
 constexpr int kTmemCols = 512;
 constexpr int kLoadWarp = 8, kMmaWarp = 9, kAllocWarp = 10;
 constexpr float kRescaleThreshold = 8.f;      // log2 units
-constexpr int kPairDefault = 0;               // CTA pairs off until measured faster (MOJO_B200_ATTN_PAIR=1)
 constexpr size_t kSmemBytes = 1024 + 2 * (size_t)kTileBytes + kRingBytes + 512;
 
 struct Params {
@@ -103,7 +102,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   uint64_t* o_full = p_full + 2;            // [2]  MMA -> softmax: last PV_t done
   uint64_t* peer_q_full = o_full + 2;       // [2]        PAIR, leader: the peer's Q tile landed (relay)
   uint64_t* peer_kv_full = peer_q_full + 2; // [kStages]  PAIR, leader: the peer's half of a K/V tile landed (relay)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_kv_full + kStages);
+  uint64_t* s_free = peer_kv_full + kStages; // [2]  softmax -> MMA: S_t(j) is in registers, the S buffer may be overwritten
+  uint64_t* p_free = s_free + 2;             // [2]  MMA -> softmax: PV_t(j) done (P_t reusable, O_t stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
@@ -179,6 +180,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       mbar_init(&p_full[t], PAIR ? 8 : 4);  // one arrive per softmax warp (of both CTAs)
       mbar_init(&o_full[t], 1);
       mbar_init(&peer_q_full[t], 1);
+      mbar_init(&s_free[t], PAIR ? 8 : 4);
+      mbar_init(&p_free[t], 1);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -215,10 +218,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         }
       }
       const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
-      uint32_t c = 0;
-      for (int j = 0; j < n_max; ++j) {
+      // ring items in the order the MMA warp first needs them: K(0) K(1) V(0) K(2) V(1) ... K(n-1) V(n-2) V(n-1)
+      const uint32_t n_items = 2u * (uint32_t)n_max;
+      {
 #pragma unroll 1
-        for (int is_v = 0; is_v < 2; ++is_v, ++c) {
+        for (uint32_t c = 0; c < n_items; ++c) {
+          int is_v, j;
+          if (c == 0) { is_v = 0; j = 0; }
+          else if (c == n_items - 1) { is_v = 1; j = n_max - 1; }
+          else if (c & 1u) { is_v = 0; j = (int)((c + 1) >> 1); }
+          else { is_v = 1; j = (int)(c >> 1) - 1; }
           // what this CTA stages of the tile: everything, or (PAIR) keys [64 rank, +64) of K as [half][64][128 B] /
           // value columns [64 rank, +64) of V as [128][128 B]
           const int box_rows = is_v ? p.box_rows_v : p.box_rows;
@@ -230,6 +239,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           const int want = p.dense ? 1 : max(0, min(rows / box_rows, (kv_len - tok0 + box_rows - 1) / box_rows));
           const uint32_t stage = ring_stage(c);
           uint8_t* dst = sKV + stage * kStageBytes;
+#ifdef MOJO_ATTN_DBG_NOTMA  // developer experiment: no K/V traffic after the first lap of the ring (results garbage)
+          if (c >= (uint32_t)kStages) {
+            if (lane == 0) {
+              mbar_wait_bounded(&kv_empty[stage], ring_parity(c) ^ 1u);
+              mbar_expect_tx(&kv_full[stage], 0);
+            }
+            __syncwarp();
+            continue;
+          }
+#endif
           if (lane == 0) {
             mbar_wait_bounded(&kv_empty[stage], ring_parity(c) ^ 1u);
             mbar_expect_tx(&kv_full[stage], (uint32_t)halves * box_bytes * (uint32_t)want);
@@ -292,24 +311,45 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       };
       auto wait_kv = [&](uint32_t c) {  // this CTA's (and the peer's) part of ring item c has landed
         mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));
-        if (PAIR) mbar_wait_bounded_cluster(&peer_kv_full[ring_stage(c)], ring_parity(c));
+        if (PAIR) mbar_wait_bounded(&peer_kv_full[ring_stage(c)], ring_parity(c));
+        tc_fence_after();
       };
-      auto qk = [&](int t, uint32_t k_stage) {  // S_t = Q_t K^T
+      // TMEM columns: S [0,128) shared by the two tiles | P_0 [128,192) P_1 [192,256) | O_0 [256,384) O_1 [384,512)
+      auto qk = [&](int t, uint32_t k_stage) {  // S = Q_t K^T
         const uint32_t qa = sQ_a + t * kTileBytes, ka = sKV_a + k_stage * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < kD / 16; ++ks) {
           const uint32_t oq = (uint32_t)(ks >> 2) * kHalfBytes + (uint32_t)(ks & 3) * 32u;
           const uint32_t ok = (uint32_t)(ks >> 2) * kKHalfStride + (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem + t * kBN, umma_desc_sw128(qa + oq, 16, 1024), umma_desc_sw128(ka + ok, 16, 1024), idesc_qk,
-                 ks > 0);
+          mma_ss(tmem, umma_desc_sw128(qa + oq, 16, 1024), umma_desc_sw128(ka + ok, 16, 1024), idesc_qk, ks > 0);
         }
       };
       auto pv = [&](int t, uint32_t v_stage, bool acc) {  // O_t (+)= P_t V
         const uint32_t va = sKV_a + v_stage * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ++ks)
-          mma_ts(tmem + 2 * kBN + t * kD, tmem + t * kBN + ks * 8, umma_desc_sw128(va + ks * 2048u, kHalfBytes, 1024),
-                 idesc_pv, acc || ks > 0);
+          mma_ts(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2) + ks * 8,
+                 umma_desc_sw128(va + ks * 2048u, kHalfBytes, 1024), idesc_pv, acc || ks > 0);
+      };
+      // The S buffer is single: a QK may only be issued once the softmax warps of the tile that owns the current
+      // content hold it in registers (s_free).  That takes ~60 cycles after S is ready, so in steady state the
+      // tensor pipe alternates  QK_1(j+1) PV_0(j) | QK_0(j+2) PV_1(j)  with no bubble: the next S of a tile is
+      // computed while that tile is still in its softmax, and P_t never aliases a buffer a QK wants.
+      int last_t = -1, last_j = 0;
+      auto issue_qk = [&](int t, int j, uint32_t k_stage) {
+        if (last_t >= 0) mbar_wait_bounded(&s_free[last_t], (uint32_t)last_j & 1u);
+        tc_fence_after();
+        qk(t, k_stage);
+        commit(&s_full[t]);
+        last_t = t;
+        last_j = j;
+      };
+      auto issue_pv = [&](int t, int j, uint32_t v_stage) {
+        mbar_wait_bounded(&p_full[t], (uint32_t)j & 1u);
+        tc_fence_after();
+        pv(t, v_stage, j > 0);
+        commit(&p_free[t]);
+        if (j == n_t[t] - 1) commit(&o_full[t]);
       };
       uint32_t c = 0;
       wait_kv(c);  // K(0)
@@ -317,47 +357,34 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       for (int t = 0; t < 2; ++t) {
         if (n_t[t] > 0) {
           mbar_wait_bounded(&q_full[t], 0);
-          if (PAIR) mbar_wait_bounded_cluster(&peer_q_full[t], 0);
-          tc_fence_after();
-          qk(t, ring_stage(c));
-          commit(&s_full[t]);
+          if (PAIR) mbar_wait_bounded(&peer_q_full[t], 0);
+          issue_qk(t, 0, ring_stage(c));
         }
       }
       commit(&kv_empty[ring_stage(c)]);
       ++c;
-      for (int j = 0; j < n_max; ++j, c += 2) {
-        const uint32_t cv = c, ck = c + 1;
-        const bool more = j + 1 < n_max;
+      uint32_t ck = 0;
+      if (1 < n_max) {
+        ck = c++;
+        wait_kv(ck);  // K(1)
+        if (1 < n_t[0]) issue_qk(0, 1, ring_stage(ck));
+      }
+      for (int j = 0; j < n_max; ++j) {
+        if (j + 1 < n_t[1]) issue_qk(1, j + 1, ring_stage(ck));
+        if (j + 1 < n_max) commit(&kv_empty[ring_stage(ck)]);  // K(j+1): both tiles' QKs are issued
+        TRACE(2, j, 0);
+        const uint32_t cv = c++;
         wait_kv(cv);  // V(j)
-        if (j < n_t[0]) {
-          if (PAIR) mbar_wait_bounded_cluster(&p_full[0], (uint32_t)j & 1u); else mbar_wait_bounded(&p_full[0], (uint32_t)j & 1u);
-          TRACE(2, j, 0);
-          tc_fence_after();
-          pv(0, ring_stage(cv), j > 0);
-          if (j == n_t[0] - 1) commit(&o_full[0]);
-        }
-        if (more) {
-          wait_kv(ck);  // K(j+1)
-          tc_fence_after();
-        }
-        if (j + 1 < n_t[0]) {
-          qk(0, ring_stage(ck));
-          commit(&s_full[0]);
-        }
+        if (j < n_t[0]) issue_pv(0, j, ring_stage(cv));
         TRACE(2, j, 1);
-        if (j < n_t[1]) {
-          if (PAIR) mbar_wait_bounded_cluster(&p_full[1], (uint32_t)j & 1u); else mbar_wait_bounded(&p_full[1], (uint32_t)j & 1u);
-          TRACE(2, j, 2);
-          tc_fence_after();
-          pv(1, ring_stage(cv), j > 0);
-          if (j == n_t[1] - 1) commit(&o_full[1]);
+        if (j + 2 < n_max) {
+          ck = c++;
+          wait_kv(ck);  // K(j+2)
+          if (j + 2 < n_t[0]) issue_qk(0, j + 2, ring_stage(ck));
         }
+        TRACE(2, j, 2);
+        if (j < n_t[1]) issue_pv(1, j, ring_stage(cv));
         commit(&kv_empty[ring_stage(cv)]);
-        if (j + 1 < n_t[1]) {
-          qk(1, ring_stage(ck));
-          commit(&s_full[1]);
-        }
-        if (more) commit(&kv_empty[ring_stage(ck)]);
         TRACE(2, j, 3);
       }
     }
@@ -370,8 +397,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
     const int n_tiles = n_t[t];
     if (n_tiles > 0) {
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem + lane_base + (uint32_t)(t * kBN);
+      const uint32_t tS = tmem + lane_base;                                       // shared S buffer
+      const uint32_t tP = tmem + lane_base + (uint32_t)(kBN + t * (kBN / 2));     // P_t (input dtype, 64 columns)
       const uint32_t tO = tmem + lane_base + (uint32_t)(2 * kBN + t * kD);
+      const uint32_t s_free_addr = PAIR ? mapa_u32(smem_u32(&s_free[t]), 0) : 0u;
+      const uint32_t p_full_addr = PAIR ? mapa_u32(smem_u32(&p_full[t]), 0) : 0u;
       const int first_row = m0 + t * kBM;
       const int row = first_row + row_local;  // row inside the sequence
       const int limit = CAUSAL ? min(kv_len - 1, off + row) : kv_len - 1;      // last key this row sees
@@ -386,8 +416,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         tc_fence_after();
         uint32_t sr[kBN];
 #pragma unroll
+#ifdef MOJO_ATTN_DBG_NOLD  // developer experiment: the softmax warps never read S from TMEM (results garbage)
+        for (int c = 0; c < kBN; ++c) sr[c] = (uint32_t)(c + j) << 20;
+#else
         for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, sr + q4 * 32);
+#endif
         tmem_wait_ld();
+        // the S buffer may be overwritten by the other tile's QK from here on
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(s_free_addr); else mbar_arrive(&s_free[t]);
+        }
         if ((warp & 3) == 0) TRACE(t, j, 1);
 
         if (ROUND_S) {  // the golden's einsum materialises the scores in the input dtype
@@ -426,7 +466,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         } else {
           const bool grow = mt > m_ref + kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
-            // PV_t(j-1) has completed (it was issued before the QK whose commit we just observed): O is stable
+            // O_t is stable once PV_t(j-1) has completed
+            mbar_wait_bounded(&p_free[t], (uint32_t)(j - 1) & 1u);
+            tc_fence_after();
             float alpha = 1.f;
             if (grow) {
               alpha = ex2_approx(m_ref - mt);
@@ -452,7 +494,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         for (int c = 0; c < kBN / 2; ++c) {  // pair c = keys 2c, 2c+1 -> one packed P word
           float2 x = fma2(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), scale2, nbase2);
           float2 e;
-          if ((c & 3) < EMU) {  // this share of the exponentials runs on the FMA pipe instead of the MUFU
+#ifdef MOJO_ATTN_DBG_NOEXP  // developer experiment: no exponentials (results garbage)
+          e = x;
+          if (true) {
+          } else if ((c & 3) < EMU) {
+#else
+          if ((c & 3) < EMU) {
+#endif  // this share of the exponentials runs on the FMA pipe instead of the MUFU
             e = ex2_emulated2(x);
           } else {
             e.x = ex2_approx(x.x);
@@ -464,14 +512,20 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         const float sum0 = sum_a.x + sum_a.y, sum1 = sum_b.x + sum_b.y;
         l += sum0 + sum1;
         if ((warp & 3) == 0) TRACE(t, j, 3);
-        tmem_st_x32(tS, sr);
-        tmem_st_x32(tS + 32, sr + 32);
+        if (j > 0) {  // PV_t(j-1) has read P_t (long done: it was issued a whole softmax ago)
+          mbar_wait_bounded(&p_free[t], (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
+        }
+#ifndef MOJO_ATTN_DBG_NOST  // developer experiment: P is never written (results garbage)
+        tmem_st_x32(tP, sr);
+        tmem_st_x32(tP + 32, sr + 32);
+#endif
 
         const int valid = kv_len - n0;
         if (valid < kBN) {
           // tail tile: V rows past the end of the sequence may hold anything (stale page rows, untouched smem);
           // P is exactly 0 there but 0 * NaN would poison O, so zero them (both warpgroups may, all store 0)
-          const uint32_t cv = 2u * (uint32_t)j + 1u;
+          const uint32_t cv = j == n_max - 1 ? 2u * (uint32_t)n_max - 1u : 2u * (uint32_t)j + 2u;  // ring item of V(j)
           mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));
           uint8_t* sv = sKV + ring_stage(cv) * kStageBytes;
           const int tid = threadIdx.x & 127;
@@ -487,7 +541,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&p_full[t]), 0)); else mbar_arrive(&p_full[t]);
+          if (PAIR) mbar_arrive_cluster(p_full_addr); else mbar_arrive(&p_full[t]);
         }
         if ((warp & 3) == 0) TRACE(t, j, 4);
       }
@@ -563,7 +617,11 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   const int group = a.num_q_heads / a.num_kv_heads;
   const bool pair_heads = group % 2 == 0;
   const bool pair_ok = pair_heads || !a.causal;
-  const bool pair = pair_ok && env_int("MOJO_B200_ATTN_PAIR", kPairDefault) != 0;
+  // measured on B200 (tools/attn_sweep.py): head pairs win everywhere (cfg3 prefill 939 -> 1113 TF/s); pairs of query
+  // blocks (no GQA sharing) only pay off once the grid is several waves deep (DiT batch >= 4 of 24 x 4096 x 128)
+  const int64_t ctas_single = ((a.max_q_len + 2 * kBM - 1) / (2 * kBM)) * a.num_q_heads * a.batch;
+  const int pair_default = pair_heads ? 1 : (ctas_single >= 8 * 148 ? 1 : 0);
+  const bool pair = pair_ok && env_int("MOJO_B200_ATTN_PAIR", pair_default) != 0;
   int box_rows_v = box_rows;
   if (pair) {  // a CTA stages 64 key rows of a K tile and all 128 key rows of one 64-column half of a V tile
     const int64_t bs = a.rows_per_block;
@@ -632,8 +690,9 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   // dense SDPA = neither
   MOJO_REQUIRE((a.causal != 0) == (a.round_scores != 0), MOJO_B200_EUNSUPPORTED,
                "attention: causal/round_scores combination not built");
-  // quarter-shares of the exponentials emulated on the FMA pipe (0..2); measured best: 1 for SDPA, 0 for prefill
-  const int emu = env_int("MOJO_B200_ATTN_EMU", a.causal ? 0 : 1);
+  // quarter-shares of the exponentials emulated on the FMA pipe (0..2).  With the shared-S schedule the softmax is no
+  // longer on the critical path and the emulation only costs issue slots and energy: 0 measured best for both ops
+  const int emu = env_int("MOJO_B200_ATTN_EMU", 0);
   const bool bf16 = a.dtype == MOJO_B200_BF16;
   if (a.causal) { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, true); else LAUNCH_SM100_EMU(__half, true); }
   else          { if (bf16) LAUNCH_SM100_EMU(__nv_bfloat16, false); else LAUNCH_SM100_EMU(__half, false); }

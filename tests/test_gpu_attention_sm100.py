@@ -34,6 +34,15 @@ def impl():
     os.environ.pop("MOJO_B200_ATTN_IMPL", None)
 
 
+@pytest.fixture(params=["single", "pair"])
+def pair(request):
+    """Force the 1-CTA kernel or the 2-CTA (cta_group::2) mode where the shape allows it (head pairs of a KV group,
+    else pairs of query blocks for non-causal attention; a causal odd group always runs single)."""
+    os.environ["MOJO_B200_ATTN_PAIR"] = "1" if request.param == "pair" else "0"
+    yield request.param
+    os.environ.pop("MOJO_B200_ATTN_PAIR", None)
+
+
 def _paged_case(q_lens, prefix_lens, Hq, Hkv, bs, dtype, seed, D=128):
     g = torch.Generator().manual_seed(seed)
     kv_lens = [a + b for a, b in zip(q_lens, prefix_lens)]
@@ -61,26 +70,41 @@ PREFILL_CASES = [
     ([200, 0, 700], [512, 40, 0], 4, 2, 32, torch.bfloat16, "ABAB"),
     ([640], [1000], 4, 1, 1024, torch.float16, "AABB"),
     ([129, 1], [3, 260], 2, 2, 8, torch.bfloat16, "AABB"),
+    # pair-mode edges: ABAB head pairs (Hkv apart), an odd group (pairs impossible: single kernel), kv tails that
+    # leave the peer's K half empty (kv % 128 <= 64) or partial, group of 8 (cfg4's shape)
+    ([513, 255], [0, 130], 8, 2, 16, torch.bfloat16, "ABAB"),
+    ([260], [33], 6, 2, 16, torch.bfloat16, "AABB"),
+    ([300], [0], 16, 2, 16, torch.float16, "AABB"),
+    ([257, 384, 192], [1, 60, 70], 4, 2, 64, torch.bfloat16, "AABB"),
 ]
 
 
 @pytest.mark.parametrize("case", PREFILL_CASES, ids=lambda c: f"q{c[0]}p{c[1]}h{c[2]}/{c[3]}bs{c[4]}{c[6]}")
-def test_prefill_tcgen05_vs_oracle(F, impl, case):
+def test_prefill_tcgen05_vs_oracle(F, impl, pair, case):
     from oracle import golden
 
     q_lens, prefix, Hq, Hkv, bs, dtype, layout = case
     q, kc, vc, cu_q, table, cu_kv = _paged_case(q_lens, prefix, Hq, Hkv, bs, dtype, seed=11)
     ref = golden.paged_prefill_gqa(q, kc, vc, cu_q, table, None, cu_kv, layout)
+    # rows of the last page past the end of a sequence hold whatever the allocator left there: poison them (the kernel
+    # must neither read them into a score that survives the mask nor let 0 * NaN reach O)
+    kc, vc = kc.clone(), vc.clone()
+    for i, (a, b) in enumerate(zip(q_lens, prefix)):
+        n = a + b
+        if n % bs:
+            blk = int(table[i, n // bs])
+            kc[blk, :, n % bs:] = float("nan")
+            vc[blk, :, n % bs:] = float("nan")
     impl("tcgen05")
     out = F.paged_prefill_gqa(q.to(DEV), kc.to(DEV), vc.to(DEV), cu_q.to(DEV), table.to(DEV), None, cu_kv.to(DEV),
                               layout, max(q_lens), max(a + b for a, b in zip(q_lens, prefix)))
     torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 2, 256, 256), (2, 3, 3, 640, 512), (1, 4, 2, 300, 777), (1, 2, 1, 129, 64)],
-                         ids=str)
+@pytest.mark.parametrize("shape", [(1, 2, 2, 256, 256), (2, 3, 3, 640, 512), (1, 4, 2, 300, 777), (1, 2, 1, 129, 64),
+                                   (1, 3, 3, 1100, 200), (2, 8, 2, 513, 40)], ids=str)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
-def test_sdpa_tcgen05_vs_oracle(F, impl, shape, dtype):
+def test_sdpa_tcgen05_vs_oracle(F, impl, pair, shape, dtype):
     from oracle import golden
 
     B, Hq, Hkv, Sq, Skv = shape
@@ -106,7 +130,7 @@ def _cfg3(T=8192, Hq=32, Hkv=8, D=128, bs=16, seed=3):
     return q, kc, vc, cu, table
 
 
-def test_prefill_full_size_properties(F, impl):
+def test_prefill_full_size_properties(F, impl, pair):
     """cfg3: T = 8192 causal, 32q/8kv, page 16 (the size bench.py quotes)."""
     T = 8192
     q, kc, vc, cu, table = _cfg3(T)
@@ -131,7 +155,7 @@ def test_prefill_full_size_properties(F, impl):
     assert not torch.equal(o2[4096:], out[4096:])
 
 
-def test_sdpa_full_size_properties(F, impl):
+def test_sdpa_full_size_properties(F, impl, pair):
     """cfg5 per-GPU slice: B2 H24 S4096 D128 non-causal, transposed-BSHD views."""
     B, H, S, D = 2, 24, 4096, 128
     g = torch.Generator(device=DEV).manual_seed(9)

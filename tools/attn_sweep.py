@@ -36,7 +36,7 @@ def main():
     g = torch.Generator().manual_seed(3)
     Hq, Hkv, D, bs = 32, 8, 128, 16
     cases = {}
-    for name, T, ctx in (("prefill8k", 8192, 0), ("chunk8k+8k", 8192, 8192), ("prefill2k x4", 2048, 0)):
+    for name, T, ctx in (("prefill8k", 8192, 0), ("chunk8k+8k", 8192, 8192), ("prefill2k x4", 2048, 0), ("prefill4k", 4096, 0), ("prefill16k", 16384, 0)):
         B = 4 if "x4" in name else 1
         kv = T + ctx
         nb = B * kv // bs + 10
@@ -50,7 +50,7 @@ def main():
         cases[name] = (lambda q=q, kc=kc, vc=vc, cu_q=cu_q, table=table, cu_kv=cu_kv, T=T, kv=kv:
                        F.paged_prefill_gqa(q, kc, vc, cu_q, table, None, cu_kv, max_q_len=T, max_total_seq_len=kv),
                        flops)
-    for name, Bd in (("sdpa b2", 2), ("sdpa b16", 16)):
+    for name, Bd in (("sdpa b1", 1), ("sdpa b2", 2), ("sdpa b4", 4), ("sdpa b16", 16)):
         H, S = 24, 4096
         qs, ks, vs = (torch.empty(Bd, S, H, D, dtype=torch.bfloat16, device=DEV).normal_().transpose(1, 2)
                       for _ in range(3))

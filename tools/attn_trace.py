@@ -14,10 +14,25 @@ buf = torch.zeros(3 * 32 * 8, dtype=torch.int64, device="cuda")
 os.environ["MOJO_B200_ATTN_TRACE_PTR"] = str(buf.data_ptr())
 from mojo_opset_b200 import functional as F  # noqa: E402
 
-Bd, H, S, D = 2, 24, 4096, 128
-qs, ks, vs = (torch.empty(Bd, S, H, D, dtype=torch.bfloat16, device="cuda").normal_().transpose(1, 2) for _ in range(3))
+D = 128
+if "--prefill" in sys.argv:  # cfg3: block 0 is the longest query block (LPT order)
+    Hq, Hkv, bs, T = 32, 8, 16, 8192
+    nb = T // bs + 10
+    kc = torch.empty(nb, Hkv, bs, D, dtype=torch.bfloat16, device="cuda").normal_()
+    vc = torch.empty(nb, Hkv, bs, D, dtype=torch.bfloat16, device="cuda").normal_()
+    q = torch.empty(T, Hq, D, dtype=torch.bfloat16, device="cuda").normal_()
+    table = torch.randperm(nb)[: T // bs].view(1, -1).to(torch.int32).cuda()
+    cu = torch.tensor([0, T], dtype=torch.int32, device="cuda")
+    run = lambda: F.paged_prefill_gqa(q, kc, vc, cu, table, None, cu, max_q_len=T, max_total_seq_len=T)
+else:
+    Bd, H, S = 2, 24, 4096
+    qs, ks, vs = (torch.empty(Bd, S, H, D, dtype=torch.bfloat16, device="cuda").normal_().transpose(1, 2) for _ in range(3))
+    run = lambda: F.sdpa(qs, ks, vs)
+if "--zeros" in sys.argv:
+    for t_ in ([q, kc, vc] if "--prefill" in sys.argv else [qs, ks, vs]):
+        t_.zero_()
 for _ in range(3):
-    F.sdpa(qs, ks, vs)
+    run()
 torch.cuda.synchronize()
 t = buf.cpu().view(3, 32, 8)
 base = int(t[0, 4, 0])
