@@ -74,8 +74,8 @@ struct Params {
 #ifdef MOJO_ATTN_TRACE
 #define TRACE(role, j, ev)                                                                                   \
   do {                                                                                                       \
-    if (p.trace && blockIdx.x == 0 && lane == 0 && (j) < 32)            \
-      p.trace[((role) * 32 + (j)) * 8 + (ev)] = clock64();                                                    \
+    if (p.trace && blockIdx.x < 2 && lane == 0 && (j) < 32 && (j) >= 0)                                      \
+      p.trace[(((role) + 3 * blockIdx.x) * 32 + (j)) * 8 + (ev)] = clock64();                                 \
   } while (0)
 #else
 #define TRACE(role, j, ev) do {} while (0)
@@ -300,12 +300,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       // K-major K operand: [64-column half][rows][128 B]; PAIR stages 64 of the 128 key rows per CTA
       constexpr uint32_t kKHalfStride = PAIR ? kHalfBytes / 2 : kHalfBytes;
       const uint32_t sQ_a = smem_u32(sQ), sKV_a = smem_u32(sKV);
-      auto mma_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-        if (PAIR) umma_ss_pair(d, ad, bd, idesc, acc); else umma_ss(d, ad, bd, idesc, acc);
-      };
-      auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t bd, uint32_t idesc, uint32_t acc) {
-        if (PAIR) umma_ts_pair(d, a, bd, idesc, acc); else umma_ts(d, a, bd, idesc, acc);
-      };
       auto commit = [&](uint64_t* bar) {
         if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
       };
@@ -315,21 +309,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         tc_fence_after();
       };
       // TMEM columns: S [0,128) shared by the two tiles | P_0 [128,192) P_1 [192,256) | O_0 [256,384) O_1 [384,512)
-      auto qk = [&](int t, uint32_t k_stage) {  // S = Q_t K^T
-        const uint32_t qa = sQ_a + t * kTileBytes, ka = sKV_a + k_stage * kStageBytes;
-#pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks) {
-          const uint32_t oq = (uint32_t)(ks >> 2) * kHalfBytes + (uint32_t)(ks & 3) * 32u;
-          const uint32_t ok = (uint32_t)(ks >> 2) * kKHalfStride + (uint32_t)(ks & 3) * 32u;
-          mma_ss(tmem, umma_desc_sw128(qa + oq, 16, 1024), umma_desc_sw128(ka + ok, 16, 1024), idesc_qk, ks > 0);
-        }
+      auto qk = [&](int t, uint32_t k_stage) {  // S = Q_t K^T: 8 K-steps in one grouped issue
+        const uint64_t qd = umma_desc_sw128(sQ_a + t * kTileBytes, 16, 1024);
+        const uint64_t kd = umma_desc_sw128(sKV_a + k_stage * kStageBytes, 16, 1024);
+        if (PAIR) umma_ss_x8_pair(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
+        else umma_ss_x8(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
       };
       auto pv = [&](int t, uint32_t v_stage, bool acc) {  // O_t (+)= P_t V
-        const uint32_t va = sKV_a + v_stage * kStageBytes;
-#pragma unroll
-        for (int ks = 0; ks < kBN / 16; ++ks)
-          mma_ts(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2) + ks * 8,
-                 umma_desc_sw128(va + ks * 2048u, kHalfBytes, 1024), idesc_pv, acc || ks > 0);
+        const uint64_t vd = umma_desc_sw128(sKV_a + v_stage * kStageBytes, kHalfBytes, 1024);
+        if (PAIR) umma_ts_x8_pair(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, acc);
+        else umma_ts_x8(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, acc);
       };
       // The S buffer is single: a QK may only be issued once the softmax warps of the tile that owns the current
       // content hold it in registers (s_free).  That takes ~60 cycles after S is ready, so in steady state the
@@ -338,6 +327,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       int last_t = -1, last_j = 0;
       auto issue_qk = [&](int t, int j, uint32_t k_stage) {
         if (last_t >= 0) mbar_wait_bounded(&s_free[last_t], (uint32_t)last_j & 1u);
+        TRACE(2, j - 1, 4 + t);  // developer timeline: the wait for the S buffer returned
         tc_fence_after();
         qk(t, k_stage);
         commit(&s_full[t]);
@@ -346,6 +336,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       };
       auto issue_pv = [&](int t, int j, uint32_t v_stage) {
         mbar_wait_bounded(&p_full[t], (uint32_t)j & 1u);
+        TRACE(2, j, 6 + t);      // developer timeline: the wait for P_t returned
         tc_fence_after();
         pv(t, v_stage, j > 0);
         commit(&p_free[t]);
@@ -543,7 +534,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         if (lane == 0) {
           if (PAIR) mbar_arrive_cluster(p_full_addr); else mbar_arrive(&p_full[t]);
         }
-        if ((warp & 3) == 0) TRACE(t, j, 4);
+        TRACE(t, j, 4 + (warp & 3));  // developer timeline: every softmax warp's arrive
       }
 
       // ---- epilogue: O / l -> out

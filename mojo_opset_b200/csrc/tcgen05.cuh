@@ -148,6 +148,79 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// ---- grouped issue: the 8 K-steps of one 128-wide product in ONE asm block ------------------------------------
+// One elect + one predicate set-up per group and the seven follow-up descriptors derived with 64-bit adds of
+// constants (the address field of a descriptor is bits [0,14) = byte address >> 4, so a step inside the 128-byte
+// swizzle atom is +2 and a jump to the second 64-column half is +half_bytes/16): the MMA warp shares its
+// sub-partition's issue slots with two softmax warps, and the per-MMA elect / R2UR / VOTEU chains of the one-by-one
+// form made the issue loop, not the tensor pipe, the bottleneck of the attention kernel.
+//   QK: A and B K-major, K-steps 0..3 inside half 0 (+2 each), 4..7 inside half 1
+#define MOJO_UMMA_SS_X8(CTA)                                                                                        \
+  asm volatile(                                                                                                     \
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"                                                             \
+      "elect.sync _|q, 0xffffffff;\n\t"                                                                             \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                                   \
+      "setp.eq.b32 t, 0, 0;\n\t"                                                                                    \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], %1, %2, %3, p;\n\t"                                        \
+      "add.s64 a, %1, 2;\n\tadd.s64 b, %2, 2;\n\t"                                                                  \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, %1, 4;\n\tadd.s64 b, %2, 4;\n\t"                                                                  \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, %1, 6;\n\tadd.s64 b, %2, 6;\n\t"                                                                  \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, %1, %5;\n\tadd.s64 b, %2, %6;\n\t"                                                                \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"                                                                    \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"                                                                    \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"                                                                    \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t}"                                         \
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "l"(a_half), "l"(b_half)                       \
+      : "memory")
+__device__ __forceinline__ void umma_ss_x8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint64_t a_half,
+                                           uint64_t b_half, uint32_t idesc, uint32_t acc) {
+  MOJO_UMMA_SS_X8("1");
+}
+__device__ __forceinline__ void umma_ss_x8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint64_t a_half,
+                                                uint64_t b_half, uint32_t idesc, uint32_t acc) {
+  MOJO_UMMA_SS_X8("2");
+}
+#undef MOJO_UMMA_SS_X8
+//   PV: A = 8 TMEM columns per K-step (+8), B MN-major (+b_step/16 per 16 keys)
+#define MOJO_UMMA_TS_X8(CTA)                                                                                        \
+  asm volatile(                                                                                                     \
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 b;\n\t.reg .b32 a;\n\t"                                                \
+      "elect.sync _|q, 0xffffffff;\n\t"                                                                             \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                                   \
+      "setp.eq.b32 t, 0, 0;\n\t"                                                                                    \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [%1], %2, %3, p;\n\t"                                      \
+      "add.u32 a, %1, 8;\n\tadd.s64 b, %2, %5;\n\t"                                                                 \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t"                                        \
+      "add.u32 a, a, 8;\n\tadd.s64 b, b, %5;\n\t"                                                                   \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t"                                        \
+      "add.u32 a, a, 8;\n\tadd.s64 b, b, %5;\n\t"                                                                   \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t"                                        \
+      "add.u32 a, a, 8;\n\tadd.s64 b, b, %5;\n\t"                                                                   \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t"                                        \
+      "add.u32 a, a, 8;\n\tadd.s64 b, b, %5;\n\t"                                                                   \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t"                                        \
+      "add.u32 a, a, 8;\n\tadd.s64 b, b, %5;\n\t"                                                                   \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t"                                        \
+      "add.u32 a, a, 8;\n\tadd.s64 b, b, %5;\n\t"                                                                   \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], [a], b, %3, t;\n\t}"                                       \
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "l"(b_step)                                    \
+      : "memory")
+__device__ __forceinline__ void umma_ts_x8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint64_t b_step,
+                                           uint32_t idesc, uint32_t acc) {
+  MOJO_UMMA_TS_X8("1");
+}
+__device__ __forceinline__ void umma_ts_x8_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint64_t b_step,
+                                                uint32_t idesc, uint32_t acc) {
+  MOJO_UMMA_TS_X8("2");
+}
+#undef MOJO_UMMA_TS_X8
+
 // ---- TMEM <-> registers (warp w of a warpgroup owns lanes 32*(w%4) .. +31; thread = lane = matrix row) -------
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
   asm volatile(

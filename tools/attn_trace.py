@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["MOJO_BACKEND"] = "b200"
 os.environ["MOJO_B200_ATTN_IMPL"] = "tcgen05"
-buf = torch.zeros(3 * 32 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(6 * 32 * 8, dtype=torch.int64, device="cuda")
 os.environ["MOJO_B200_ATTN_TRACE_PTR"] = str(buf.data_ptr())
 from mojo_opset_b200 import functional as F  # noqa: E402
 
@@ -34,12 +34,12 @@ if "--zeros" in sys.argv:
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-t = buf.cpu().view(3, 32, 8)
+t = buf.cpu().view(6, 32, 8)
 base = int(t[0, 4, 0])
-names = ["sm0", "sm1", "mma"]
+names = ["sm0", "sm1", "mma", "sm0'", "sm1'", "mma'"]  # primed: block 1 (the peer CTA in pair mode)
 for j in range(4, 14):
-    for r in range(3):
-        ev = [int(x) - base for x in t[r, j, :5]]
+    for r in range(6):
+        ev = [int(x) - base for x in t[r, j, :8]]
         print(f"j={j:2d} {names[r]}: " + " ".join(f"{e:7d}" for e in ev))
 print("softmax events: 0 S ready | 1 S in regs | 2 max+rescale done | 3 exp done | 4 arrived")
-print("mma events:     0 P0 ready | 1 PV0+QK0 issued | 2 P1 ready | 3 PV1+QK1 issued")
+print("mma events:     0 QK1(j+1) issued | 1 PV0(j) issued | 2 QK0(j+2) issued | 3 PV1(j) issued | 4 S free for QK0(j+1) | 5 S free for QK1(j+1) | 6 P0(j) seen | 7 P1(j) seen")

@@ -21,7 +21,7 @@ template <int MODE> __device__ __forceinline__ void wait(uint64_t* bar, uint32_t
 
 constexpr int kRounds = 256;
 
-template <int MODE>
+template <int MODE, bool DYN>
 __global__ void __launch_bounds__(256, 1) latency_kernel(long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -83,10 +83,15 @@ __global__ void __launch_bounds__(256, 1) latency_kernel(long long* out) {
   //     MMA warp waits bar5 then issues the next 8.  Period = the hand-off chain.
   if (warp == 0) {
     long long t0 = clock64();
+    volatile int* dyn = reinterpret_cast<volatile int*>(out + 8);  // zeros the compiler cannot see through
     for (int r = 0; r < kRounds; ++r) {
+      // DYN: operand bases and the accumulate flag come from memory each round, as the ring stage / tile index do in
+      // the attention kernel: the descriptors cannot be hoisted or kept in uniform registers
+      const uint32_t ad = DYN ? a + dyn[r & 1] : a, bd = DYN ? b + dyn[(r + 1) & 1] : b, td = DYN ? tmem + dyn[r & 1] : tmem;
+      const bool accd = DYN ? dyn[r & 1] != 0 : false;
       for (int ks = 0; ks < 8; ++ks)
-        umma_ss(tmem, umma_desc_sw128(a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                umma_desc_sw128(b + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), idesc, ks > 0);
+        umma_ss(td, umma_desc_sw128(ad + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                umma_desc_sw128(bd + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), idesc, accd || ks > 0);
       umma_commit(&bar[4]);
       wait<MODE>(&bar[5], r & 1);
       tc_fence_after();
@@ -102,9 +107,7 @@ __global__ void __launch_bounds__(256, 1) latency_kernel(long long* out) {
       for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, sr + q4 * 32);
       tmem_wait_ld();
       tc_fence_before();
-      uint32_t x = 0;
-      for (int i = 0; i < 128; ++i) x ^= sr[i];
-      if (x == 0x12345) out[7] = 1;
+      if ((sr[0] ^ sr[37] ^ sr[127]) == 0x12345) out[7] = 1;
       if (warp == 5) { __syncwarp(); if (lane == 0) mbar_arrive(&bar[5]); }
     }
   }
@@ -113,9 +116,9 @@ __global__ void __launch_bounds__(256, 1) latency_kernel(long long* out) {
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-template <int MODE> void run(const char* name) {
-  long long* d; cudaMalloc(&d, 64); cudaMemset(d, 0, 64);
-  auto kern = latency_kernel<MODE>;
+template <int MODE, bool DYN> void run(const char* name) {
+  long long* d; cudaMalloc(&d, 128); cudaMemset(d, 0, 128);
+  auto kern = latency_kernel<MODE, DYN>;
   const int smem = 1024 + 65536 + 128;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int r = 0; r < 2; ++r) kern<<<2, 256, smem>>>(d);
@@ -127,7 +130,7 @@ template <int MODE> void run(const char* name) {
 }
 
 int main() {
-  run<0>("try_wait ");
-  run<1>("test_wait");
+  run<0, false>("try_wait, static operands ");
+  run<0, true>("try_wait, dynamic operands");
   return 0;
 }
