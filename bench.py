@@ -227,8 +227,17 @@ def run_b200(args):
             decode_events.append(ev)
         layer_step(res, res_tables[L], res_metas[L], caches[L][0], caches[L][1], ev)
 
+    # every number is the MEDIAN of `--repeats` timed regions of exactly K steps each (a 4 ms region on a fresh box is
+    # at the mercy of one host hiccup; all samples are reported)
+    def median(xs):
+        xs = sorted(xs)
+        return xs[len(xs) // 2]
+
     with ClockSampler(local_rank) as clocks:
-        ms_resident = timed(resident_step, args.steps, args.warmup)
+        resident_samples = []
+        for _ in range(args.repeats):
+            resident_samples.append(timed(resident_step, args.steps, args.warmup))
+        ms_resident = median(resident_samples)
         # keep the GPU busy long enough for the sampler to see clocks under load on short runs
         extra_rounds = 0
         while len(clocks.rows) < 3 and extra_rounds < 20:
@@ -237,7 +246,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             extra_rounds += 1
     torch.cuda.synchronize()
-    decode_ms = sum(a.elapsed_time(b) for a, b in decode_events) / max(len(decode_events), 1)
+    decode_ms = median([a.elapsed_time(b) for a, b in decode_events])  # per-launch CUDA-event time, all repeats
 
     # ---- e2e: host buffers in, host results out, every step.  A serving loop overlaps PCIe with compute, so the step
     # is a 2-deep pipeline over three streams: step i+1's inputs travel host->device (ONE packed pinned buffer: all
@@ -316,7 +325,8 @@ def run_b200(args):
             ms = t.item()
         return ms
 
-    ms_e2e = e2e_timed(args.steps, args.warmup)
+    e2e_samples = [e2e_timed(args.steps, args.warmup) for _ in range(args.repeats)]
+    ms_e2e = median(e2e_samples)
 
     peaks = load_peaks()
     algo_bytes = decode_bytes(cfg, B)
@@ -360,6 +370,9 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "pipeline": "2-deep: packed pinned H2D | compute | D2H on three streams"},
         "gpu_launches": launches_per_step * args.steps,
+        "timing": {"repeats": args.repeats, "stat": "median over repeats of a timed region of exactly `steps` steps",
+                   "resident_ms_samples": [round(x, 4) for x in resident_samples],
+                   "e2e_ms_samples": [round(x, 4) for x in e2e_samples]},
         "roofline": {"kernel": "paged_decode_mma_kernel (+ reduce)", "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "frac_of_8TBs_nominal": achieved / 8000.0, "peak_source": peaks["source"],
@@ -489,6 +502,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=4, help="distinct KV caches rotated across steps")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
