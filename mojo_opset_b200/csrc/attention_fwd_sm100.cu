@@ -100,9 +100,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   uint64_t* s_full = kv_empty + kStages;    // [2]  MMA -> softmax: S_t ready
   uint64_t* p_full = s_full + 2;            // [2]  softmax -> MMA: P_t written (and S_t consumed)
   uint64_t* o_full = p_full + 2;            // [2]  MMA -> softmax: last PV_t done
-  uint64_t* peer_q_full = o_full + 2;       // [2]        PAIR, leader: the peer's Q tile landed (relay)
-  uint64_t* peer_kv_full = peer_q_full + 2; // [kStages]  PAIR, leader: the peer's half of a K/V tile landed (relay)
-  uint64_t* s_free = peer_kv_full + kStages; // [2]  softmax -> MMA: S_t(j) is in registers, the S buffer may be overwritten
+  uint64_t* s_free = o_full + 2;            // [2]  softmax -> MMA: S_t(j) is in registers, the S buffer may be overwritten
   uint64_t* p_free = s_free + 2;             // [2]  MMA -> softmax: PV_t(j) done (P_t reusable, O_t stable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
@@ -175,18 +173,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&q_full[t], 1);
+      mbar_init(&q_full[t], (PAIR && rank == 0) ? 2 : 1);  // leader: own TMA + the peer's relay
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], PAIR ? 8 : 4);  // one arrive per softmax warp (of both CTAs)
       mbar_init(&o_full[t], 1);
-      mbar_init(&peer_q_full[t], 1);
       mbar_init(&s_free[t], PAIR ? 8 : 4);
       mbar_init(&p_free[t], 1);
     }
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_full[s], (PAIR && rank == 0) ? 2 : 1);
       mbar_init(&kv_empty[s], 1);
-      mbar_init(&peer_kv_full[s], 1);
     }
     mbar_fence_init();
   }
@@ -277,7 +273,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       // ---------------------------------------------------------------------------- peer relay: "my halves landed"
       // in the order the leader's MMA warp waits for them
       if (lane == 0) {
-        const uint32_t pq = mapa_u32(smem_u32(peer_q_full), 0), pkv = mapa_u32(smem_u32(peer_kv_full), 0);
+        const uint32_t pq = mapa_u32(smem_u32(q_full), 0), pkv = mapa_u32(smem_u32(kv_full), 0);
         auto relay_kv = [&](uint32_t c) {
           mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));
           mbar_arrive_cluster(pkv + ring_stage(c) * 8u);
@@ -291,8 +287,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         }
         for (uint32_t c = 1; c < 2u * (uint32_t)n_max; ++c) relay_kv(c);
       }
-    } else if (warp == kMmaWarp) {
-      // ---------------------------------------------------------------------------- MMA issuer (whole warp, converged)
+    } else if ((warp == kMmaWarp || warp == kAllocWarp) && rank == 0) {
+      // ---------------------------------------------------------------------------- MMA issuers (whole warps, converged)
+      // Two of them: warp 9 issues every S = Q K^T, warp 10 every O += P V.  The products touch different TMEM
+      // columns and every dependence between them already goes through an mbarrier (S free, P full, P free, ring
+      // stages), so they need no common program order - and one warp doing all the waits, commits and descriptor
+      // set-up of a step measured ~3300 cycles per step against 2048 cycles of tensor work: the issuer, not the
+      // tensor pipe, was the bottleneck.
       constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
       constexpr int kM = PAIR ? 2 * kBM : kBM;  // PAIR: rows of both CTAs in one instruction
       constexpr uint32_t idesc_qk = umma_idesc_f16(kFmt, kM, kBN, 0, 0);
@@ -303,80 +304,67 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       auto commit = [&](uint64_t* bar) {
         if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
       };
-      auto wait_kv = [&](uint32_t c) {  // this CTA's (and the peer's) part of ring item c has landed
+      auto wait_kv = [&](uint32_t c) {  // ring item c has landed (PAIR: in both CTAs - the relay arrives on the same barrier)
         mbar_wait_bounded(&kv_full[ring_stage(c)], ring_parity(c));
-        if (PAIR) mbar_wait_bounded(&peer_kv_full[ring_stage(c)], ring_parity(c));
         tc_fence_after();
       };
+      // ring items: 0 = K(0); then odd c = K((c+1)/2), even c = V(c/2-1); the last one is V(n-1)
+      const uint32_t n_items = 2u * (uint32_t)n_max;
+      auto item_k = [&](int j) { return j == 0 ? 0u : 2u * (uint32_t)j - 1u; };
+      auto item_v = [&](int j) { return j == n_max - 1 ? n_items - 1u : 2u * (uint32_t)j + 2u; };
       // TMEM columns: S [0,128) shared by the two tiles | P_0 [128,192) P_1 [192,256) | O_0 [256,384) O_1 [384,512)
-      auto qk = [&](int t, uint32_t k_stage) {  // S = Q_t K^T: 8 K-steps in one grouped issue
-        const uint64_t qd = umma_desc_sw128(sQ_a + t * kTileBytes, 16, 1024);
-        const uint64_t kd = umma_desc_sw128(sKV_a + k_stage * kStageBytes, 16, 1024);
-        if (PAIR) umma_ss_x8_pair(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
-        else umma_ss_x8(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
-      };
-      auto pv = [&](int t, uint32_t v_stage, bool acc) {  // O_t (+)= P_t V
-        const uint64_t vd = umma_desc_sw128(sKV_a + v_stage * kStageBytes, kHalfBytes, 1024);
-        if (PAIR) umma_ts_x8_pair(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, acc);
-        else umma_ts_x8(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, acc);
-      };
-      // The S buffer is single: a QK may only be issued once the softmax warps of the tile that owns the current
-      // content hold it in registers (s_free).  That takes ~60 cycles after S is ready, so in steady state the
-      // tensor pipe alternates  QK_1(j+1) PV_0(j) | QK_0(j+2) PV_1(j)  with no bubble: the next S of a tile is
-      // computed while that tile is still in its softmax, and P_t never aliases a buffer a QK wants.
-      int last_t = -1, last_j = 0;
-      auto issue_qk = [&](int t, int j, uint32_t k_stage) {
-        if (last_t >= 0) mbar_wait_bounded(&s_free[last_t], (uint32_t)last_j & 1u);
-        TRACE(2, j - 1, 4 + t);  // developer timeline: the wait for the S buffer returned
-        tc_fence_after();
-        qk(t, k_stage);
-        commit(&s_full[t]);
-        last_t = t;
-        last_j = j;
-      };
-      auto issue_pv = [&](int t, int j, uint32_t v_stage) {
-        mbar_wait_bounded(&p_full[t], (uint32_t)j & 1u);
-        TRACE(2, j, 6 + t);      // developer timeline: the wait for P_t returned
-        tc_fence_after();
-        pv(t, v_stage, j > 0);
-        commit(&p_free[t]);
-        if (j == n_t[t] - 1) commit(&o_full[t]);
-      };
-      uint32_t c = 0;
-      wait_kv(c);  // K(0)
+      if (warp == kMmaWarp) {
+        // The S buffer is single: a QK may only be issued once the softmax warps of the tile that owns the current
+        // content hold it in registers (s_free), ~60 cycles after S is ready.  Order: QK_0(0) QK_1(0) QK_0(1) QK_1(1) ...
+        // so the next S of a tile is computed while that tile is still in its softmax.
+        int last_t = -1, last_j = 0;
+        auto issue_qk = [&](int t, int j, uint32_t k_stage) {
+          if (last_t >= 0) mbar_wait_bounded(&s_free[last_t], (uint32_t)last_j & 1u);
+          TRACE(2, j, 4 + t);  // developer timeline: the wait for the S buffer returned
+          tc_fence_after();
+          const uint64_t qd = umma_desc_sw128(sQ_a + t * kTileBytes, 16, 1024);
+          const uint64_t kd = umma_desc_sw128(sKV_a + k_stage * kStageBytes, 16, 1024);
+          if (PAIR) umma_ss_x8_pair(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
+          else umma_ss_x8(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
+          commit(&s_full[t]);
+          TRACE(2, j, 2 * t);
+          last_t = t;
+          last_j = j;
+        };
+        for (int j = 0; j < n_max; ++j) {
+          const uint32_t ck = item_k(j);
+          wait_kv(ck);
+          if (j == 0) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (n_t[t] > 0) {
-          mbar_wait_bounded(&q_full[t], 0);
-          if (PAIR) mbar_wait_bounded(&peer_q_full[t], 0);
-          issue_qk(t, 0, ring_stage(c));
+            for (int t = 0; t < 2; ++t)
+              if (n_t[t] > 0) {
+                mbar_wait_bounded(&q_full[t], 0);
+                tc_fence_after();
+              }
+          }
+          if (j < n_t[0]) issue_qk(0, j, ring_stage(ck));
+          if (j < n_t[1]) issue_qk(1, j, ring_stage(ck));
+          commit(&kv_empty[ring_stage(ck)]);
         }
-      }
-      commit(&kv_empty[ring_stage(c)]);
-      ++c;
-      uint32_t ck = 0;
-      if (1 < n_max) {
-        ck = c++;
-        wait_kv(ck);  // K(1)
-        if (1 < n_t[0]) issue_qk(0, 1, ring_stage(ck));
-      }
-      for (int j = 0; j < n_max; ++j) {
-        if (j + 1 < n_t[1]) issue_qk(1, j + 1, ring_stage(ck));
-        if (j + 1 < n_max) commit(&kv_empty[ring_stage(ck)]);  // K(j+1): both tiles' QKs are issued
-        TRACE(2, j, 0);
-        const uint32_t cv = c++;
-        wait_kv(cv);  // V(j)
-        if (j < n_t[0]) issue_pv(0, j, ring_stage(cv));
-        TRACE(2, j, 1);
-        if (j + 2 < n_max) {
-          ck = c++;
-          wait_kv(ck);  // K(j+2)
-          if (j + 2 < n_t[0]) issue_qk(0, j + 2, ring_stage(ck));
+      } else {
+        auto issue_pv = [&](int t, int j, uint32_t v_stage) {
+          mbar_wait_bounded(&p_full[t], (uint32_t)j & 1u);
+          TRACE(2, j, 6 + t);      // developer timeline: the wait for P_t returned
+          tc_fence_after();
+          const uint64_t vd = umma_desc_sw128(sKV_a + v_stage * kStageBytes, kHalfBytes, 1024);
+          if (PAIR) umma_ts_x8_pair(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, j > 0);
+          else umma_ts_x8(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, j > 0);
+          commit(&p_free[t]);
+          if (j == n_t[t] - 1) commit(&o_full[t]);
+          TRACE(2, j, 1 + 2 * t);
+        };
+        for (int j = 0; j < n_max; ++j) {
+          const uint32_t cv = item_v(j);
+          wait_kv(cv);
+          if (j < n_t[0]) issue_pv(0, j, ring_stage(cv));
+          if (j < n_t[1]) issue_pv(1, j, ring_stage(cv));
+          commit(&kv_empty[ring_stage(cv)]);
         }
-        TRACE(2, j, 2);
-        if (j < n_t[1]) issue_pv(1, j, ring_stage(cv));
-        commit(&kv_empty[ring_stage(cv)]);
-        TRACE(2, j, 3);
       }
     }
     __syncwarp();
