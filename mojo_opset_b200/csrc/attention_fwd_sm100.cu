@@ -2,33 +2,34 @@
 // TMA.  head_dim 128, bf16/fp16, paged (power-of-two pages >= 8) or dense strided K/V.
 //
 // One CTA per SM (384 threads) owns TWO 128-row query tiles of one (sequence, query head) and walks the KV
-// sequence in 128-key tiles; the two tiles ping-pong so that the tensor pipe works on one while the other is
-// in its softmax:
+// sequence in 128-key tiles.  TMEM (all 512 columns): S [0,128) - ONE score buffer handed back and forth between
+// the two tiles | P_0 [128,192) P_1 [192,256) (input dtype) | O_0 [256,384) O_1 [384,512).
 //
-//   warp  8      TMA producer: Q tiles once, then K(0) V(0) K(1) V(1) ... through a ring of 32 KB stages
-//                (full/empty mbarriers).  A paged tile is gathered page by page through the block table, one
-//                cp.async.bulk.tensor per (page, 64-column half), landing in the 128B-swizzled K-major layout
-//                UMMA reads ([half][key][128 B]).
-//   warp  9      MMA issuer (one thread): S_t = Q_t K^T   (SS, M128 N128 K16 x 8,  K-major A and B)
-//                                         O_t += P_t V    (TS, A = P from TMEM, B = V as an MN-major operand)
-//                issue order  PV_0(j) QK_0(j+1) PV_1(j) QK_1(j+1): tcgen05 executes in order, so a commit after
-//                QK_t(j+1) also certifies PV_t(j) - which is what lets the softmax warps rescale O in place.
+//   warp  8      TMA producer: Q tiles once, then the K/V tiles in the order the issuers first need them
+//                (K(0) K(1) V(0) K(2) V(1) ...) through a ring of stages (full/empty mbarriers).  A paged tile is
+//                gathered page by page through the block table, one cp.async.bulk.tensor per (page, 64-column
+//                half), landing in the 128B-swizzled K-major layout UMMA reads ([half][key][128 B]).
+//   warp  9      QK issuer:  S = Q_t K(j)^T  (SS, M128 N128 K16 x 8 in one grouped asm block), order
+//                QK_0(0) QK_1(0) QK_0(1) QK_1(1) ...; a QK is issued as soon as the softmax warps of the tile that
+//                owns the current S hold it in registers (s_free, ~60 cycles after S is ready) - i.e. the NEXT S of
+//                a tile is computed while that tile is still in its softmax.
+//   warp 10      PV issuer:  O_t += P_t V(j)  (TS, A = P_t from TMEM, B = V as an MN-major operand) once P_t(j) is
+//                written; also the TMEM allocator.  QK and PV touch different TMEM columns and every dependence
+//                between them goes through an mbarrier, so two warps share the issue work (one warp doing every
+//                wait / commit / descriptor set-up measured 3300 cycles per step against 2048 cycles of tensor work).
 //   warps 0-3    softmax of tile 0, warps 4-7 softmax of tile 1: thread = query row = TMEM lane.  S row from
-//                TMEM (tcgen05.ld) -> [round to the input dtype, as the golden's einsum] -> * scale, mask ->
+//                TMEM (tcgen05.ld) -> release S -> [round to the input dtype, as the golden's einsum] -> mask ->
 //                running max with LAZY rescaling (O and l are only rescaled when the max grows by more than
-//                2^8, so almost every tile skips the O read-modify-write) -> exp2 -> P (input dtype) written
-//                over S in TMEM (tcgen05.st) -> arrive.  Epilogue: O row / l -> out.
-//   warp 10      TMEM allocation (all 512 columns: S0 S1 O0 O1, P_t aliases the first 64 columns of S_t).
+//                2^8, after waiting for PV_t(j-1)) -> exp2 -> P_t (tcgen05.st) -> arrive.  Epilogue: O row / l -> out.
 //
 // PAIR = true: the same kernel on a 2-CTA cluster with cta_group::2 MMAs (M = 256: the two CTAs' query tiles in one
 // instruction).  The two CTAs work on two query heads of one KV group (GQA, even group) or on two adjacent query
 // blocks of one head (non-causal), so they need the SAME K/V tiles and each stages only half of every tile: CTA r
 // holds keys [64 r, 64 r + 64) of a K tile (the N split of S = Q K^T) and value columns [64 r, 64 r + 64) of a V
-// tile (the N split of O = P V).  Per CTA the shared-memory operand traffic of a QK MMA drops from 8 KB to 6 KB
-// (below the 128 B/clk the SS form is limited by), of a PV MMA from 4 KB to 2 KB, and L2 -> SM traffic halves.
-// The leader CTA issues every MMA; TMA completion of the peer's halves reaches it through a relay (the peer's
-// otherwise idle MMA warp: wait local barrier -> remote arrive); the peer's softmax warps arrive remotely on the
-// leader's P barrier; commits multicast to both CTAs.
+// tile (the N split of O = P V): shared-memory fills and L2 -> SM traffic halve and the ring is twice as deep.
+// The leader CTA issues every MMA; TMA completion of the peer's halves reaches the leader's ring barriers through a
+// relay (the peer's otherwise idle warp 9: wait local barrier -> remote arrive); the peer's softmax warps arrive
+// remotely on the leader's barriers; commits multicast to both CTAs.
 //
 // FLOPs = 4 * D * (unmasked (q, k) pairs) per query head; the roofline is the bf16 tensor peak.
 #include <cmath>
