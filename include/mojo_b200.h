@@ -180,6 +180,27 @@ MOJO_B200_API int mojo_b200_paged_prefill_gqa(
     float softmax_scale, int gqa_interleave, int is_causal, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * MojoPagedPrefillSWA.forward                       mojo_opset/core/operators/attention.py:533-640
+ * MojoPagedDecodeSWA.forward                        mojo_opset/core/operators/attention.py:645-742
+ *   (decode = one query token per sequence: cu_q_lens = 0..B, cu_total_seq_lens = cumulative total_seq_lens)
+ *
+ * Same tensors as mojo_b200_paged_prefill_gqa.  On top of the causal limit a key is visible iff
+ * key + local_window_size >= position  or  key < global_window_size  (_generate_window_mask, attention.py:507-531);
+ * -1 stands for None; both -1 = plain causal attention.  KV tiles no row of a query block can see are never loaded.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_paged_prefill_swa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* cu_q_lens,
+    const int32_t* cu_total_seq_lens, const int32_t* block_tables, void* out,
+    int64_t total_q_tokens, int batch, int num_q_heads, int num_kv_heads, int head_dim,
+    int64_t num_blocks, int block_size, int max_blocks_per_seq, int64_t table_stride,
+    int64_t max_q_len, int64_t max_kv_len,
+    int64_t q_stride_t, int64_t q_stride_h, int64_t o_stride_t, int64_t o_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    float softmax_scale, int gqa_interleave, int is_causal, int local_window_size, int global_window_size,
+    int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * MojoSdpa.forward                                  mojo_opset/core/operators/attention.py:466-501
  *
  * query [B, Hq, Sq, D], key/value [B, Hkv, Skv, D] through (b, h, s) strides (D contiguous), no mask,

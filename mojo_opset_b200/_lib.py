@@ -45,6 +45,8 @@ SIGNATURES = {
     "mojo_b200_paged_decode_gqa": (I, [P, P, P, P, P, P, P, Z, I, I, I, I, L, I, I, L, L] + [L] * 10 + [F, I, I, I, P]),
     "mojo_b200_paged_prefill_gqa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10
                                     + [F, I, I, I, P]),
+    "mojo_b200_paged_prefill_swa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10
+                                    + [F, I, I, I, I, I, P]),
     "mojo_b200_sdpa": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, I, P]),
     "mojo_b200_norm_rope_store_kv": (I, [P, P, P, P, P, F, P, P, P, P, P, P, P, L, I, P, P, I, L, I, I, I, I, L, I]
                                      + [L] * 17 + [I, I, P]),

@@ -4,7 +4,9 @@ from .operators.activation import B200Gelu
 from .operators.activation import B200Silu
 from .operators.activation import B200SwiGLU
 from .operators.attention import B200PagedDecodeGQA
+from .operators.attention import B200PagedDecodeSWA
 from .operators.attention import B200PagedPrefillGQA
+from .operators.attention import B200PagedPrefillSWA
 from .operators.attention import B200Sdpa
 from .operators.compute_with_comm import B200GemmAllReduce
 from .operators.fused_attention_input import B200NormRoPEStoreKV
@@ -23,6 +25,8 @@ __all__ = [
     "B200SwiGLU",
     "B200PagedDecodeGQA",
     "B200PagedPrefillGQA",
+    "B200PagedPrefillSWA",
+    "B200PagedDecodeSWA",
     "B200Sdpa",
     "B200GemmAllReduce",
     "B200NormRoPEStoreKV",

@@ -7,7 +7,9 @@ from .operators.activation import MojoGelu
 from .operators.activation import MojoSilu
 from .operators.activation import MojoSwiGLU
 from .operators.attention import MojoPagedDecodeGQA
+from .operators.attention import MojoPagedDecodeSWA
 from .operators.attention import MojoPagedPrefillGQA
+from .operators.attention import MojoPagedPrefillSWA
 from .operators.attention import MojoSdpa
 from .operators.compute_with_comm import MojoGemmAllReduce
 from .operators.fused_attention_input import MojoNormRoPEStoreKV
@@ -29,6 +31,8 @@ __all__ = [
     "MojoSwiGLU",
     "MojoPagedDecodeGQA",
     "MojoPagedPrefillGQA",
+    "MojoPagedPrefillSWA",
+    "MojoPagedDecodeSWA",
     "MojoSdpa",
     "MojoGemmAllReduce",
     "MojoNormRoPEStoreKV",

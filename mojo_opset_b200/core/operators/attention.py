@@ -106,6 +106,67 @@ class MojoPagedPrefillGQA(_PagedGQABase, MojoOperator):
         return MojoOperator.forward(self)
 
 
+class _PagedSWABase(_PagedGQABase):
+    def _init_swa(self, is_causal, gqa_layout, global_window_size, local_window_size) -> None:
+        self._init_paged(is_causal, gqa_layout)
+        self.gqa_interleave = gqa_layout == "ABAB"
+        self.global_window_size = global_window_size
+        self.local_window_size = local_window_size
+
+    def extra_repr(self) -> str:
+        return (f"is_causal={self.is_causal}, gqa_layout={self.gqa_layout}, "
+                f"global_window_size={self.global_window_size}, local_window_size={self.local_window_size}")
+
+
+class MojoPagedPrefillSWA(_PagedSWABase, MojoOperator):
+    """``MojoPagedPrefillGQA`` with a sliding window (reference ``attention.py:533-643``): on top of the causal limit a
+    key is visible iff ``key + local_window_size >= position`` or ``key < global_window_size``
+    (``_generate_window_mask``, ``:507-531``); a window left ``None`` contributes nothing, both ``None`` = causal."""
+
+    def __init__(self, is_causal: bool = True, gqa_layout: str = "AABB", global_window_size: Optional[int] = None,
+                 local_window_size: Optional[int] = None):
+        super().__init__()
+        self._init_swa(is_causal, gqa_layout, global_window_size, local_window_size)
+
+    def forward(
+        self,
+        query: torch.Tensor,
+        key_cache: torch.Tensor,
+        value_cache: torch.Tensor,
+        cu_q_lens: torch.Tensor,
+        block_table: torch.Tensor,
+        softmax_scale: Optional[float] = None,
+        cu_total_seq_lens: Optional[torch.Tensor] = None,
+        *,
+        max_q_len: Optional[int] = None,
+        max_total_seq_len: Optional[int] = None,
+    ):
+        return MojoOperator.forward(self)
+
+
+class MojoPagedDecodeSWA(_PagedSWABase, MojoOperator):
+    """``MojoPagedDecodeGQA`` with the same window rule for the single query token at position ``seq_len - 1``
+    (reference ``attention.py:645-745``)."""
+
+    def __init__(self, is_causal: bool = True, gqa_layout: str = "AABB", global_window_size: Optional[int] = None,
+                 local_window_size: Optional[int] = None):
+        super().__init__()
+        self._init_swa(is_causal, gqa_layout, global_window_size, local_window_size)
+
+    def forward(
+        self,
+        query: torch.Tensor,
+        key_cache: torch.Tensor,
+        value_cache: torch.Tensor,
+        total_seq_lens: torch.Tensor,
+        block_table: torch.Tensor,
+        softmax_scale: Optional[float] = None,
+        *,
+        max_total_seq_len: Optional[int] = None,
+    ):
+        return MojoOperator.forward(self)
+
+
 class MojoSdpa(MojoOperator):
     """Dense non-causal SDPA ``[B,Hq,Sq,D] x [B,Hkv,Skv,D]`` (inputs may be strided views)."""
 

@@ -13,6 +13,7 @@
 //         -> * scale -> causal / length mask -> online softmax (log2 domain) -> P rounded to the input dtype
 //         -> O += P V (fp32) -> O / l.
 // FLOPs = 4 * D * (number of unmasked (q, k) pairs) per query head.
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -40,6 +41,9 @@ struct AttnParams {
   int64_t q_st, q_sh, q_sb, o_st, o_sh, o_sb;
   float scale_log2;  // softmax_scale * log2(e)
   int interleave, causal, dense, stages, round_scores;
+  // sliding-window attention (MojoPagedPrefillSWA / MojoPagedDecodeSWA): on top of the causal limit a key is visible
+  // iff key + win_local >= position or key < win_global; -1 = that window is not set (both -1: plain causal)
+  int win_local, win_global;
 };
 
 template <typename T, int D, bool SPLIT_HALVES>
@@ -81,6 +85,17 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
   const int n_tiles = n_end > 0 ? (n_end + kTile - 1) / kTile : 0;
   if (n_tiles == 0) return;  // rows that see no key keep the zeros the output was initialised with
   const int kvh = p.interleave ? hq % p.num_kv_heads : hq / p.group;
+  // windows: row at position pos sees keys >= pos - win_local (if set) and keys < win_global (if set)
+  const bool has_win = p.causal && (p.win_local >= 0 || p.win_global >= 0);
+  const int win_g = has_win && p.win_global >= 0 ? p.win_global : 0;
+  auto win_lo = [&](int row) -> int {  // first key of the row's local window
+    if (!has_win) return INT_MIN;
+    return p.win_local >= 0 ? off + row - p.win_local : INT_MAX;
+  };
+  // KV tiles between the global prefix and the first row's local window are invisible to the whole CTA: producer and
+  // consumers skip them alike (the same predicate on both sides keeps the ring in step)
+  const int cta_lo = win_lo(m0);
+  auto tile_live = [&](int it) -> bool { return it * kTile < win_g || it * kTile + kTile - 1 >= cta_lo; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -102,9 +117,11 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
     }
     const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
     const uint32_t box_bytes = (uint32_t)box_rows * D * 2;
-    for (int it = 0; it < n_tiles; ++it) {
-      const int stage = it % stages;
-      const uint32_t phase = (uint32_t)(it / stages) & 1u;
+    for (int it = 0, use = 0; it < n_tiles; ++it) {
+      if (!tile_live(it)) continue;
+      const int stage = use % stages;
+      const uint32_t phase = (uint32_t)(use / stages) & 1u;
+      ++use;
       const int tok0 = it * kTile;
       const int want = min(boxes_per_tile, (kv_len - tok0 + box_rows - 1) / box_rows);
       int blk = 0, row_in_page = 0;
@@ -176,12 +193,16 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
   const int lim_hi = p.causal ? min(kv_len - 1, off + row_hi) : kv_len - 1;
   const int warp_first_lim = p.causal ? off + m0 + warp * 16 : kv_len - 1;       // most restrictive row
   const int warp_last_lim = p.causal ? off + m0 + warp * 16 + 15 : kv_len - 1;   // least restrictive row
+  const int lo_lo = win_lo(row_lo), lo_hi = win_lo(row_hi);                      // this thread's rows' local windows
+  const int warp_min_lo = win_lo(m0 + warp * 16), warp_max_lo = win_lo(m0 + warp * 16 + 15);
   const float scale_log2 = p.scale_log2;
   const bool round_scores = p.round_scores != 0;
 
-  for (int it = 0; it < n_tiles; ++it) {
-    const int stage = it % stages;
-    const uint32_t phase = (uint32_t)(it / stages) & 1u;
+  for (int it = 0, use = 0; it < n_tiles; ++it) {
+    if (!tile_live(it)) continue;
+    const int stage = use % stages;
+    const uint32_t phase = (uint32_t)(use / stages) & 1u;
+    ++use;
     const int n0 = it * kTile;
     uint8_t* sk = tiles + (size_t)stage * 2 * TILE_BYTES;
     uint8_t* sv = sk + TILE_BYTES;
@@ -189,7 +210,8 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
 
     mbar_wait(&full[stage], phase);
 
-    if (n0 <= warp_last_lim) {  // otherwise none of this warp's rows sees the tile (causal)
+    // otherwise none of this warp's rows sees the tile (causal limit / between the global prefix and the windows)
+    if (n0 <= warp_last_lim && (n0 < win_g || n0 + kTile - 1 >= warp_min_lo)) {
       const int valid = kv_len - n0;
       if (valid < kTile) {
         // tail tile: zero the V rows past the end of the sequence (every warp reads all 64 rows, and each
@@ -221,7 +243,8 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
       }
 
       // ---- rounding, scale, mask
-      const bool need_mask = n0 + kTile - 1 > warp_first_lim || valid < kTile;
+      const bool need_mask = n0 + kTile - 1 > warp_first_lim || valid < kTile ||
+                             (has_win && !(n0 >= warp_max_lo || n0 + kTile - 1 < win_g));
       float tile_lo = -INFINITY, tile_hi = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -231,7 +254,7 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
           v *= scale_log2;
           if (need_mask) {
             const int key = n0 + j * 8 + 2 * c + (e & 1);
-            if (key > (e < 2 ? lim_lo : lim_hi)) v = -INFINITY;
+            if (key > (e < 2 ? lim_lo : lim_hi) || (key < (e < 2 ? lo_lo : lo_hi) && key >= win_g)) v = -INFINITY;
           }
           s[j][e] = v;
           if (e < 2) tile_lo = fmaxf(tile_lo, v); else tile_hi = fmaxf(tile_hi, v);
@@ -409,14 +432,14 @@ __global__ void prefill_zero_unseen_rows_kernel(void* out, const int32_t* cu_q, 
 
 }  // namespace mojo
 
-extern "C" int mojo_b200_paged_prefill_gqa(
+static int paged_prefill_impl(
     const void* query, const void* key_cache, const void* value_cache, const int32_t* cu_q_lens,
     const int32_t* cu_total_seq_lens, const int32_t* block_tables, void* out, int64_t total_q_tokens, int batch,
     int num_q_heads, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq,
     int64_t table_stride, int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h,
     int64_t o_stride_t, int64_t o_stride_h, int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
     int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t, float softmax_scale, int gqa_interleave,
-    int is_causal, int dtype, void* stream) {
+    int is_causal, int win_local, int win_global, int dtype, void* stream) {
   using namespace mojo;
   (void)max_kv_len;
   MOJO_REQUIRE(total_q_tokens >= 0 && batch >= 0 && num_q_heads > 0 && num_kv_heads > 0 && head_dim > 0 &&
@@ -446,7 +469,7 @@ extern "C" int mojo_b200_paged_prefill_gqa(
   }
   if (max_q_len <= 0 || max_q_len > total_q_tokens) max_q_len = total_q_tokens;
 
-  {  // tcgen05/TMEM kernel when the shape is covered
+  if (win_local < 0 && win_global < 0) {  // tcgen05/TMEM kernel when the shape is covered (it has no window mask)
     AttnSm100Args a;
     memset(&a, 0, sizeof(a));
     a.q = query; a.out = out; a.q_rows = total_q_tokens; a.q_st = q_stride_t; a.q_sh = q_stride_h;
@@ -472,11 +495,46 @@ extern "C" int mojo_b200_paged_prefill_gqa(
   p.q_st = q_stride_t; p.q_sh = q_stride_h; p.q_sb = 0; p.o_st = o_stride_t; p.o_sh = o_stride_h; p.o_sb = 0;
   p.scale_log2 = softmax_scale * kLog2eF;
   p.interleave = gqa_interleave ? 1 : 0; p.causal = 1; p.dense = 0; p.round_scores = 1;
+  p.win_local = win_local; p.win_global = win_global;
 
   KvDesc kv{key_cache, value_cache, kc_stride_b, kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t,
             block_size, num_blocks, num_kv_heads};
   dim3 grid((unsigned)((max_q_len + kBM - 1) / kBM), (unsigned)num_q_heads, (unsigned)batch);
   return launch_attn_mma(kv, p, head_dim, dtype, grid, (cudaStream_t)stream);
+}
+
+extern "C" int mojo_b200_paged_prefill_gqa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* cu_q_lens,
+    const int32_t* cu_total_seq_lens, const int32_t* block_tables, void* out, int64_t total_q_tokens, int batch,
+    int num_q_heads, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq,
+    int64_t table_stride, int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h,
+    int64_t o_stride_t, int64_t o_stride_h, int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t, float softmax_scale, int gqa_interleave,
+    int is_causal, int dtype, void* stream) {
+  return paged_prefill_impl(query, key_cache, value_cache, cu_q_lens, cu_total_seq_lens, block_tables, out,
+                            total_q_tokens, batch, num_q_heads, num_kv_heads, head_dim, num_blocks, block_size,
+                            max_blocks_per_seq, table_stride, max_q_len, max_kv_len, q_stride_t, q_stride_h, o_stride_t,
+                            o_stride_h, kc_stride_b, kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t,
+                            softmax_scale, gqa_interleave, is_causal, -1, -1, dtype, stream);
+}
+
+extern "C" int mojo_b200_paged_prefill_swa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* cu_q_lens,
+    const int32_t* cu_total_seq_lens, const int32_t* block_tables, void* out, int64_t total_q_tokens, int batch,
+    int num_q_heads, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq,
+    int64_t table_stride, int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h,
+    int64_t o_stride_t, int64_t o_stride_h, int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t, float softmax_scale, int gqa_interleave,
+    int is_causal, int local_window_size, int global_window_size, int dtype, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(local_window_size >= -1 && global_window_size >= -1, MOJO_B200_EINVAL,
+               "paged_prefill_swa: window sizes must be >= 0, or -1 for None");
+  return paged_prefill_impl(query, key_cache, value_cache, cu_q_lens, cu_total_seq_lens, block_tables, out,
+                            total_q_tokens, batch, num_q_heads, num_kv_heads, head_dim, num_blocks, block_size,
+                            max_blocks_per_seq, table_stride, max_q_len, max_kv_len, q_stride_t, q_stride_h, o_stride_t,
+                            o_stride_h, kc_stride_b, kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t,
+                            softmax_scale, gqa_interleave, is_causal, local_window_size, global_window_size, dtype,
+                            stream);
 }
 
 extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* value, void* out, int batch,
@@ -524,6 +582,7 @@ extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* va
   p.o_st = o_stride_s; p.o_sh = o_stride_h; p.o_sb = o_stride_b;
   p.scale_log2 = softmax_scale * kLog2eF;
   p.interleave = 0; p.causal = 0; p.dense = 1; p.round_scores = 0;
+  p.win_local = p.win_global = -1;
 
   KvDesc kv{key, value, k_stride_b, k_stride_h, k_stride_s, v_stride_b, v_stride_h, v_stride_s, kv_len, batch,
             num_kv_heads};

@@ -354,7 +354,11 @@ def paged_prefill_gqa(
     max_q_len: Optional[int] = None,
     max_total_seq_len: Optional[int] = None,
     is_causal: bool = True,
+    local_window_size: Optional[int] = None,
+    global_window_size: Optional[int] = None,
 ) -> torch.Tensor:
+    """``local_window_size`` / ``global_window_size`` (``MojoPagedPrefillSWA``): on top of the causal limit a key is
+    visible iff ``key + local >= position`` or ``key < global``; both ``None`` = plain causal attention."""
     dev = _require_cuda(query, key_cache, value_cache, cu_q_lens, block_tables, cu_total_seq_lens)
     lib = _lib.load()
     if query.dim() != 3:
@@ -379,16 +383,55 @@ def paged_prefill_gqa(
     q_hint = total_q if max_q_len is None else min(int(max_q_len), total_q)
     kv_cap = max_blocks * block_size
     kv_hint = kv_cap if max_total_seq_len is None else min(int(max_total_seq_len), kv_cap)
-    rc = lib.mojo_b200_paged_prefill_gqa(
+    common = (
         q.data_ptr(), kc.data_ptr(), vc.data_ptr(), cu_q.data_ptr(), _lib.ptr(cu_kv), tables.data_ptr(),
         out.data_ptr(), total_q, batch, num_q_heads, num_kv_heads, head_dim, num_blocks, block_size, max_blocks,
         tables.stride(0) if max_blocks else 0, q_hint, kv_hint,
         q.stride(0), q.stride(1), out.stride(0), out.stride(1),
         kc.stride(0), kc.stride(1), kc.stride(2), vc.stride(0), vc.stride(1), vc.stride(2),
-        float(softmax_scale), 1 if gqa_layout == "ABAB" else 0, 1 if is_causal else 0, _lib.dtype_id(query.dtype),
-        _lib.stream_ptr(dev))
-    _lib.check(lib, rc, "paged_prefill_gqa")
+        float(softmax_scale), 1 if gqa_layout == "ABAB" else 0, 1 if is_causal else 0)
+    if local_window_size is None and global_window_size is None:
+        rc = lib.mojo_b200_paged_prefill_gqa(*common, _lib.dtype_id(query.dtype), _lib.stream_ptr(dev))
+        _lib.check(lib, rc, "paged_prefill_gqa")
+    else:
+        for name, w in (("local_window_size", local_window_size), ("global_window_size", global_window_size)):
+            if w is not None and int(w) < 0:
+                raise ValueError(f"paged_prefill_swa: {name} must be >= 0 or None")
+        rc = lib.mojo_b200_paged_prefill_swa(
+            *common, -1 if local_window_size is None else int(local_window_size),
+            -1 if global_window_size is None else int(global_window_size), _lib.dtype_id(query.dtype),
+            _lib.stream_ptr(dev))
+        _lib.check(lib, rc, "paged_prefill_swa")
     return out
+
+
+def paged_decode_swa(
+    query: torch.Tensor,
+    key_cache: torch.Tensor,
+    value_cache: torch.Tensor,
+    total_seq_lens: torch.Tensor,
+    block_tables: torch.Tensor,
+    softmax_scale: Optional[float] = None,
+    gqa_layout: str = "AABB",
+    max_total_seq_len: Optional[int] = None,
+    local_window_size: Optional[int] = None,
+    global_window_size: Optional[int] = None,
+) -> torch.Tensor:
+    """``MojoPagedDecodeSWA``: one query token per sequence = the windowed prefill with ``q_len = 1`` rows
+    (``cu_q_lens = 0..B``, cumulative ``total_seq_lens``; both built on the device, no host read).  Without any window
+    this is ``paged_decode_gqa`` (the split-KV streaming kernel)."""
+    if local_window_size is None and global_window_size is None:
+        return paged_decode_gqa(query, key_cache, value_cache, total_seq_lens, block_tables, softmax_scale, gqa_layout,
+                                max_total_seq_len)
+    dev = _require_cuda(query, key_cache, value_cache, total_seq_lens, block_tables)
+    if query.dim() != 3:
+        raise ValueError("paged_decode_swa: query must be [batch, num_q_heads, head_dim]")
+    batch = query.shape[0]
+    cu_q = torch.arange(batch + 1, dtype=torch.int32, device=dev)
+    cu_kv = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
+    torch.cumsum(total_seq_lens.clamp_min(0), 0, out=cu_kv[1:])
+    return paged_prefill_gqa(query, key_cache, value_cache, cu_q, block_tables, softmax_scale, cu_kv, gqa_layout, 1,
+                             max_total_seq_len, True, local_window_size, global_window_size)
 
 
 def sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Optional[float] = None,

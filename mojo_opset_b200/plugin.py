@@ -27,6 +27,8 @@ from typing import Dict
 OPS = (
     "PagedDecodeGQA",
     "PagedPrefillGQA",
+    "PagedPrefillSWA",
+    "PagedDecodeSWA",
     "Sdpa",
     "StorePagedKVCache",
     "ResidualAddRMSNorm",

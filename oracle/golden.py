@@ -127,6 +127,74 @@ def paged_prefill_gqa(query, key_cache, value_cache, cu_q_lens, block_tables, so
 
 
 # --------------------------------------------------------------------------------------------------
+# f4  MojoPagedPrefillSWA.forward / MojoPagedDecodeSWA.forward   reference core/operators/attention.py:533-745
+# --------------------------------------------------------------------------------------------------
+def window_mask(q_len: int, kv_len: int, local_window_size=None, global_window_size=None):
+    """``[q_len, kv_len]`` bool, True = visible (reference ``_generate_window_mask``, attention.py:507-531): causal
+    with offset ``kv_len - q_len`` AND (inside the local window OR inside the global prefix); a window that is ``None``
+    contributes nothing, both ``None`` leaves the causal mask."""
+    pos = torch.arange(q_len).unsqueeze(1) + (kv_len - q_len)
+    key = torch.arange(kv_len).unsqueeze(0)
+    visible = key <= pos
+    if local_window_size is None and global_window_size is None:
+        return visible
+    windows = torch.zeros(q_len, kv_len, dtype=torch.bool)
+    if local_window_size is not None:
+        windows |= pos <= key + local_window_size
+    if global_window_size is not None:
+        windows |= key < global_window_size
+    return visible & windows
+
+
+def paged_prefill_swa(query, key_cache, value_cache, cu_q_lens, block_table, softmax_scale=None,
+                      cu_total_seq_lens=None, gqa_layout: str = "AABB", is_causal: bool = True,
+                      local_window_size=None, global_window_size=None):
+    """Scores by a batched matmul in the input dtype, upcast, scaled (attention.py:611); window mask; softmax pieces in
+    fp32 with P rounded to the input dtype before P V (:620-624); P V in the input dtype, upcast, divided by l (:635)."""
+    total_q, num_q_heads, head_dim = query.shape
+    num_kv_heads = key_cache.shape[1]
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(head_dim)
+    head_map = _kv_head_of_q_head(num_q_heads, num_kv_heads, gqa_layout, query.device)
+    out = torch.zeros(total_q, num_q_heads, head_dim, dtype=query.dtype, device=query.device)
+    cu_q = cu_q_lens.tolist()
+    cu_kv = cu_q if cu_total_seq_lens is None else cu_total_seq_lens.tolist()
+    tables = block_table.tolist()
+    for b in range(len(cu_q) - 1):
+        lo, hi = cu_q[b], cu_q[b + 1]
+        q_len, kv_len = hi - lo, cu_kv[b + 1] - cu_kv[b]
+        if q_len == 0 or kv_len <= 0:
+            continue
+        if tables[b][0] < 0:
+            raise ValueError("Paged prefill requires a valid block table for rows with kv lens > 0.")
+        k = _gather_sequence_kv(key_cache, tables[b], kv_len, query.dtype)[:, head_map]    # [kv, Hq, D]
+        v = _gather_sequence_kv(value_cache, tables[b], kv_len, query.dtype)[:, head_map]
+        q = query[lo:hi].permute(1, 0, 2)                                                  # [Hq, q, D]
+        scores = torch.bmm(q, k.permute(1, 2, 0)).float() * softmax_scale                  # [Hq, q, kv]
+        if is_causal:
+            vis = window_mask(q_len, kv_len, local_window_size, global_window_size).to(scores.device)
+            scores = torch.where(vis, scores, float("-inf"))
+        scores = scores - scores.max(dim=-1, keepdim=True).values
+        p = torch.exp(scores)
+        l = p.sum(dim=-1, keepdim=True)
+        o = torch.bmm(p.to(query.dtype), v.permute(1, 0, 2)).float() / l
+        out[lo:hi] = o.permute(1, 0, 2).to(out.dtype)
+    return out
+
+
+def paged_decode_swa(query, key_cache, value_cache, total_seq_lens, block_table, softmax_scale=None,
+                     gqa_layout: str = "AABB", local_window_size=None, global_window_size=None):
+    """One query token per sequence at position ``seq_len - 1`` (attention.py:672-742): the prefill rule with
+    ``q_len = 1``; rows with ``seq_len <= 0`` stay zero."""
+    lens = [max(int(n), 0) for n in total_seq_lens.tolist()]
+    batch = query.shape[0]
+    cu_q = torch.arange(batch + 1, dtype=torch.int32)
+    cu_kv = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32)
+    return paged_prefill_swa(query, key_cache, value_cache, cu_q, block_table, softmax_scale, cu_kv, gqa_layout, True,
+                             local_window_size, global_window_size)
+
+
+# --------------------------------------------------------------------------------------------------
 # a3  MojoSdpa.forward                      reference core/operators/attention.py:466-501
 # --------------------------------------------------------------------------------------------------
 def sdpa(query, key, value, attn_mask=None, scale: Optional[float] = None, enable_gqa: bool = False):

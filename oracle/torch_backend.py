@@ -38,6 +38,28 @@ class TorchPagedPrefillGQA(core.MojoPagedPrefillGQA):
                                         cu_total_seq_lens, self.gqa_layout, self.is_causal)
 
 
+class TorchPagedPrefillSWA(core.MojoPagedPrefillSWA):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, query, key_cache, value_cache, cu_q_lens, block_table, softmax_scale=None,
+                cu_total_seq_lens=None, *, max_q_len=None, max_total_seq_len=None):
+        core.operators.attention.assert_paged_prefill_contract(cu_q_lens, block_table, cu_total_seq_lens)
+        return golden.paged_prefill_swa(query, key_cache, value_cache, cu_q_lens, block_table, softmax_scale,
+                                        cu_total_seq_lens, self.gqa_layout, self.is_causal, self.local_window_size,
+                                        self.global_window_size)
+
+
+class TorchPagedDecodeSWA(core.MojoPagedDecodeSWA):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, query, key_cache, value_cache, total_seq_lens, block_table, softmax_scale=None, *,
+                max_total_seq_len=None):
+        core.operators.attention.assert_paged_decode_contract(block_table, total_seq_lens)
+        assert self.is_causal, "golden restatement covers the causal path only"
+        return golden.paged_decode_swa(query, key_cache, value_cache, total_seq_lens, block_table, softmax_scale,
+                                       self.gqa_layout, self.local_window_size, self.global_window_size)
+
+
 class TorchSdpa(core.MojoSdpa):
     supported_platforms_list = ["b200", "meta_device"]
 

@@ -97,6 +97,54 @@ def gen_prefill():
     torch.save(cases, os.path.join(HERE, "paged_prefill_gqa.pt"))
 
 
+def gen_swa():
+    """MojoPagedPrefillSWA / MojoPagedDecodeSWA (reference attention.py:533-745): local / global / both / no window,
+    windows shorter and longer than the sequences, cached prefixes, ABAB, a zero-length row.  Written by
+    ``python tests/golden/make_golden.py swa`` (only this fixture is regenerated)."""
+    cases = []
+    specs = [
+        # name, q_lens, ctx_lens, Hq, Hkv, D, bs, dtype, layout, local, global
+        ("local_only", [150, 70, 5], None, 4, 2, 128, 16, torch.bfloat16, "AABB", 32, None),
+        ("local_global_prefix", [90, 130], [137, 16], 4, 2, 128, 16, torch.bfloat16, "AABB", 48, 8),
+        ("global_only_abab", [77, 0, 40], [0, 0, 25], 4, 2, 128, 32, torch.bfloat16, "ABAB", None, 20),
+        ("wide_windows", [64, 31], None, 4, 1, 64, 16, torch.float16, "AABB", 1000, 1000),
+        ("no_window", [40, 21], [3, 0], 4, 2, 128, 16, torch.bfloat16, "AABB", None, None),
+        ("local_zero", [33], [100], 2, 2, 128, 16, torch.bfloat16, "AABB", 0, 4),
+    ]
+    for i, (name, q_lens, ctx, hq, hkv, d, bs, dtype, layout, local, glob) in enumerate(specs):
+        gen = torch.Generator().manual_seed(8000 + i)
+        kv_lens = q_lens if ctx is None else [a + b for a, b in zip(q_lens, ctx)]
+        kc, vc, table = paged_cache(gen, kv_lens, hkv, d, bs, dtype)
+        q = torch.randn(sum(q_lens), hq, d, generator=gen).to(dtype)
+        cu_q = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0)), dtype=torch.int32)
+        cu_kv = None if ctx is None else torch.tensor([0] + list(torch.tensor(kv_lens).cumsum(0)), dtype=torch.int32)
+        scale = 1.0 / math.sqrt(d)
+        out = torch_op(ref.MojoPagedPrefillSWA, is_causal=True, gqa_layout=layout, global_window_size=glob,
+                       local_window_size=local)(q, kc, vc, cu_q, table, softmax_scale=scale, cu_total_seq_lens=cu_kv)
+        cases.append(dict(op="prefill", name=name, gqa_layout=layout, local_window_size=local, global_window_size=glob,
+                          query=q, key_cache=kc, value_cache=vc, cu_q_lens=cu_q, block_table=table,
+                          softmax_scale=scale, cu_total_seq_lens=cu_kv, out=out))
+    dspecs = [
+        # name, lens, Hq, Hkv, D, bs, dtype, layout, local, global
+        ("dec_local", [137, 1, 128, 95, 16], 8, 2, 128, 16, torch.bfloat16, "AABB", 32, None),
+        ("dec_both_abab", [260, 33, 17], 8, 2, 128, 32, torch.bfloat16, "ABAB", 64, 4),
+        ("dec_padseq_global", [0, 150, 0, 9], 8, 1, 128, 16, torch.bfloat16, "AABB", 16, 100),
+        ("dec_fp16_d64", [70, 41], 4, 4, 64, 16, torch.float16, "AABB", 7, 3),
+    ]
+    for i, (name, lens, hq, hkv, d, bs, dtype, layout, local, glob) in enumerate(dspecs):
+        gen = torch.Generator().manual_seed(8100 + i)
+        kc, vc, table = paged_cache(gen, lens, hkv, d, bs, dtype)
+        q = torch.randn(len(lens), hq, d, generator=gen).to(dtype)
+        seq = torch.tensor(lens, dtype=torch.int32)
+        scale = 1.0 / math.sqrt(d)
+        out = torch_op(ref.MojoPagedDecodeSWA, is_causal=True, gqa_layout=layout, global_window_size=glob,
+                       local_window_size=local)(q, kc, vc, seq, table, softmax_scale=scale)
+        cases.append(dict(op="decode", name=name, gqa_layout=layout, local_window_size=local, global_window_size=glob,
+                          query=q, key_cache=kc, value_cache=vc, total_seq_lens=seq, block_table=table,
+                          softmax_scale=scale, out=out))
+    torch.save(cases, os.path.join(HERE, "paged_swa.pt"))
+
+
 def gen_sdpa():
     cases = []
     gen = torch.Generator().manual_seed(3000)
@@ -265,6 +313,10 @@ def gen_act():
 if __name__ == "__main__":
     torch.manual_seed(0)
     print("reference:", ref.__file__, "torch", torch.__version__, "threads", torch.get_num_threads())
-    for fn in (gen_decode, gen_prefill, gen_sdpa, gen_store_kv, gen_norm, gen_rope, gen_act):
+    if "swa" in sys.argv[1:]:  # later addition: regenerate this fixture alone (the others stay byte-identical)
+        gen_swa()
+        print("wrote gen_swa")
+        sys.exit(0)
+    for fn in (gen_decode, gen_prefill, gen_sdpa, gen_store_kv, gen_norm, gen_rope, gen_act, gen_swa):
         fn()
         print("wrote", fn.__name__)

@@ -41,6 +41,7 @@ NORM = load_golden("rmsnorm.pt")
 ROPE = load_golden("apply_rope.pt")
 ROTARY = load_golden("rotary_embedding.pt")
 ACT = load_golden("activation.pt")
+SWA = load_golden("paged_swa.pt")
 
 
 def _tol(dtype):
@@ -64,6 +65,53 @@ def test_paged_prefill(ops, case):
              _cuda(case["block_tables"]), softmax_scale=case["softmax_scale"],
              cu_total_seq_lens=_cuda(case["cu_total_seq_lens"]))
     torch.testing.assert_close(out.cpu().float(), case["out"].float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("case", SWA, ids=_ids(SWA))
+def test_paged_swa(ops, case):
+    """MojoPagedPrefillSWA / MojoPagedDecodeSWA against the reference's outputs, through the op classes -> C ABI."""
+    win = dict(global_window_size=case["global_window_size"], local_window_size=case["local_window_size"])
+    if case["op"] == "prefill":
+        op = ops.MojoPagedPrefillSWA(is_causal=True, gqa_layout=case["gqa_layout"], **win)
+        assert type(op).__name__ == "B200PagedPrefillSWA"
+        out = op(_cuda(case["query"]), _cuda(case["key_cache"]), _cuda(case["value_cache"]), _cuda(case["cu_q_lens"]),
+                 _cuda(case["block_table"]), softmax_scale=case["softmax_scale"],
+                 cu_total_seq_lens=_cuda(case["cu_total_seq_lens"]))
+    else:
+        op = ops.MojoPagedDecodeSWA(is_causal=True, gqa_layout=case["gqa_layout"], **win)
+        assert type(op).__name__ == "B200PagedDecodeSWA"
+        out = op(_cuda(case["query"]), _cuda(case["key_cache"]), _cuda(case["value_cache"]),
+                 _cuda(case["total_seq_lens"]), _cuda(case["block_table"]), softmax_scale=case["softmax_scale"])
+    assert out.shape == case["out"].shape
+    torch.testing.assert_close(out.cpu().float(), case["out"].float(), atol=2e-2, rtol=2e-2)
+
+
+def test_paged_swa_long_window_skips_tiles(ops):
+    """A long sequence with a short window: the kernel loads only the KV tiles a query block can see (global prefix +
+    the tiles under the window); the result must match the oracle, and - property - must not depend on the keys and
+    values outside every window."""
+    from oracle import golden
+
+    g = torch.Generator().manual_seed(77)
+    Hq, Hkv, D, bs, T, local, glob = 4, 2, 128, 16, 1500, 100, 40
+    nb = T // bs + 3
+    kc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16)
+    vc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16)
+    q = torch.randn(T, Hq, D, generator=g).to(torch.bfloat16)
+    table = torch.randperm(nb, generator=g)[: (T + bs - 1) // bs].view(1, -1).to(torch.int32)
+    cu = torch.tensor([0, T], dtype=torch.int32)
+    op = ops.MojoPagedPrefillSWA(global_window_size=glob, local_window_size=local)
+    out = op(_cuda(q), _cuda(kc), _cuda(vc), _cuda(cu), _cuda(table))
+    ref = golden.paged_prefill_swa(q, kc, vc, cu, table, None, None, "AABB", True, local, glob)
+    torch.testing.assert_close(out.cpu().float(), ref.float(), atol=2e-2, rtol=2e-2)
+    # rows >= 1000 see keys < 40 and keys >= 900 only: rewriting keys 64..799 cannot change them (bit-exact)
+    kc2, vc2 = kc.clone(), vc.clone()
+    mid = table[0, 4:50].long()
+    kc2[mid] = torch.randn(kc2[mid].shape, generator=g).to(torch.bfloat16)
+    vc2[mid] = torch.randn(vc2[mid].shape, generator=g).to(torch.bfloat16)
+    out2 = op(_cuda(q), _cuda(kc2), _cuda(vc2), _cuda(cu), _cuda(table))
+    assert torch.equal(out2[1000:], out[1000:])
+    assert not torch.equal(out2[:900], out[:900])
 
 
 @pytest.mark.parametrize("case", SDPA, ids=_ids(SDPA))

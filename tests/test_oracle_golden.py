@@ -22,6 +22,7 @@ NORM = load_golden("rmsnorm.pt")
 ROPE = load_golden("apply_rope.pt")
 ROTARY = load_golden("rotary_embedding.pt")
 ACT = load_golden("activation.pt")
+SWA = load_golden("paged_swa.pt")
 
 
 @pytest.mark.parametrize("case", DECODE, ids=_ids(DECODE))
@@ -37,6 +38,33 @@ def test_prefill_bit_exact(case):
                                    case["block_tables"], case["softmax_scale"], case["cu_total_seq_lens"],
                                    case["gqa_layout"])
     assert torch.equal(out, case["out"])
+
+
+@pytest.mark.parametrize("case", SWA, ids=_ids(SWA))
+def test_swa_bit_exact(case):
+    """MojoPagedPrefillSWA / MojoPagedDecodeSWA (reference attention.py:533-745): the restatement against the
+    reference's own outputs."""
+    win = dict(local_window_size=case["local_window_size"], global_window_size=case["global_window_size"])
+    if case["op"] == "prefill":
+        out = golden.paged_prefill_swa(case["query"], case["key_cache"], case["value_cache"], case["cu_q_lens"],
+                                       case["block_table"], case["softmax_scale"], case["cu_total_seq_lens"],
+                                       case["gqa_layout"], True, **win)
+    else:
+        out = golden.paged_decode_swa(case["query"], case["key_cache"], case["value_cache"], case["total_seq_lens"],
+                                      case["block_table"], case["softmax_scale"], case["gqa_layout"], **win)
+    assert torch.equal(out, case["out"])
+
+
+def test_window_mask_matches_definition():
+    """Row at position p sees key k iff k <= p and (p <= k + local or k < global) - brute force."""
+    for q_len, kv_len, local, glob in [(5, 9, 2, None), (7, 7, None, 3), (4, 20, 6, 2), (3, 3, None, None), (6, 10, 0, 0)]:
+        m = golden.window_mask(q_len, kv_len, local, glob)
+        for t in range(q_len):
+            p = kv_len - q_len + t
+            for k in range(kv_len):
+                win = True if local is None and glob is None else (
+                    (local is not None and p <= k + local) or (glob is not None and k < glob))
+                assert bool(m[t, k]) == (k <= p and win)
 
 
 @pytest.mark.parametrize("case", SDPA, ids=_ids(SDPA))
