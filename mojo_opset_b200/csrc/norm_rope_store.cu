@@ -77,6 +77,53 @@ __global__ void __launch_bounds__(256) norm_rope_store_kernel(const NrsArgs a) {
   const int64_t tok = blockIdx.x;
   const int sl = threadIdx.x % LPH, hs = threadIdx.x / LPH;
 
+  // ---- this lane's role inside a head and its cos / sin / norm-weight slices
+  const int nope = D - a.rope_dim, half = a.rope_dim / 2;
+  const int e0 = sl * 8;
+  const bool rotary = e0 >= nope;
+  const bool second = e0 >= nope + half;
+  const int partner_lane = second ? sl - half / 8 : sl + half / 8;
+  float cs[8], sn[8];
+  if (rotary) {
+    // 8-element slices are 8 * sizeof(C) aligned (checked by the entry point): vector loads
+    struct alignas(8 * sizeof(C)) Slice { C v[8]; };
+    const Slice cv = *reinterpret_cast<const Slice*>((const C*)a.cos + tok * a.cos_t + (e0 - nope));
+    const Slice sv = *reinterpret_cast<const Slice*>((const C*)a.sin + tok * a.cos_t + (e0 - nope));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cs[i] = DType<C>::to_f(cv.v[i]);
+      sn[i] = DType<C>::to_f(sv.v[i]);
+    }
+  }
+  Row8 wq_p = {{0u, 0u, 0u, 0u}}, wk_p = wq_p;  // norm weights stay packed (registers) until used
+  if (NORM) {
+    wq_p = *reinterpret_cast<const Row8*>((const T*)a.wq + e0);
+    wk_p = *reinterpret_cast<const Row8*>((const T*)a.wk + e0);
+  }
+
+  // ---- the rows of the first kPre trips are requested BEFORE the page-slot lookup below: that lookup is a chain of
+  // four to eight dependent loads (binary search over cu_q_lens, context length, block table) and a CTA only lives
+  // for three trips at Qwen3 shapes, so with the rows issued after it about half of a CTA's life was lookup latency
+  // (prefill T = 8192: 67 us = 0.47 of the HBM peak)
+  const int total = a.hq + 2 * a.hkv;
+  constexpr int kPre = 3;
+  auto head_src = [&](int h, int& kind, int& hh) -> const T* {
+    kind = h >= total ? 2 : h < a.hq ? 0 : (h < a.hq + a.hkv ? 1 : 2);  // 0: q head, 1: k head, 2: v head / idle
+    hh = kind == 0 ? h : (h < a.hq + a.hkv ? h - a.hq : h - a.hq - a.hkv);
+    return kind == 0 ? (const T*)a.q + tok * a.q_t + (int64_t)hh * a.q_h
+         : kind == 1 ? (const T*)a.k + tok * a.k_t + (int64_t)hh * a.k_h
+                     : (const T*)a.v + tok * a.v_t + (int64_t)hh * a.v_h;
+  };
+  Row8 pre[kPre];
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) {
+    pre[i] = Row8{{0u, 0u, 0u, 0u}};
+    int kind, hh;
+    const int h = i * HSLOTS + hs;
+    const T* src = head_src(h, kind, hh);
+    if (h < total) pre[i] = *reinterpret_cast<const Row8*>(src + e0);
+  }
+
   // ---- page slot of this token (warp-uniform; every thread computes it, a handful of cached loads)
   int64_t kc_off = -1, vc_off = -1;
   {
@@ -113,43 +160,13 @@ __global__ void __launch_bounds__(256) norm_rope_store_kernel(const NrsArgs a) {
     }
   }
 
-  // ---- this lane's role inside a head and its cos / sin / norm-weight slices
-  const int nope = D - a.rope_dim, half = a.rope_dim / 2;
-  const int e0 = sl * 8;
-  const bool rotary = e0 >= nope;
-  const bool second = e0 >= nope + half;
-  const int partner_lane = second ? sl - half / 8 : sl + half / 8;
-  float cs[8], sn[8];
-  if (rotary) {
-    // 8-element slices are 8 * sizeof(C) aligned (checked by the entry point): vector loads
-    struct alignas(8 * sizeof(C)) Slice { C v[8]; };
-    const Slice cv = *reinterpret_cast<const Slice*>((const C*)a.cos + tok * a.cos_t + (e0 - nope));
-    const Slice sv = *reinterpret_cast<const Slice*>((const C*)a.sin + tok * a.cos_t + (e0 - nope));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      cs[i] = DType<C>::to_f(cv.v[i]);
-      sn[i] = DType<C>::to_f(sv.v[i]);
-    }
-  }
-  Row8 wq_p = {{0u, 0u, 0u, 0u}}, wk_p = wq_p;  // norm weights stay packed (registers) until used
-  if (NORM) {
-    wq_p = *reinterpret_cast<const Row8*>((const T*)a.wq + e0);
-    wk_p = *reinterpret_cast<const Row8*>((const T*)a.wk + e0);
-  }
-
-  const int total = a.hq + 2 * a.hkv;
-  // every lane of a warp runs every trip (the shuffles below are full-warp); lanes past the last head idle as "v"
-  for (int h0 = 0; h0 < total; h0 += HSLOTS) {
+  auto process = [&](int h0, const Row8* fetched) {
     const int h = h0 + hs;
     const bool active = h < total;
-    // kind 0: q head, 1: k head, 2: v head (no norm, no RoPE)
-    const int kind = !active ? 2 : h < a.hq ? 0 : (h < a.hq + a.hkv ? 1 : 2);
-    const int hh = kind == 0 ? h : (kind == 1 ? h - a.hq : h - a.hq - a.hkv);
-    const T* src = kind == 0 ? (const T*)a.q + tok * a.q_t + (int64_t)hh * a.q_h
-                 : kind == 1 ? (const T*)a.k + tok * a.k_t + (int64_t)hh * a.k_h
-                             : (const T*)a.v + tok * a.v_t + (int64_t)hh * a.v_h;
+    int kind, hh;
+    const T* src = head_src(h, kind, hh);
     Row8 row = {{0u, 0u, 0u, 0u}};
-    if (active) row = *reinterpret_cast<const Row8*>(src + e0);
+    if (fetched) row = *fetched; else if (active) row = *reinterpret_cast<const Row8*>(src + e0);
     if (active && kind == 2 && vc_off >= 0)
       *reinterpret_cast<Row8*>((T*)a.vc + vc_off + (int64_t)hh * a.vc_h + e0) = row;
     // a warp holds 32 / LPH heads that may be of different kinds: the shuffles below are executed by all lanes
@@ -176,7 +193,7 @@ __global__ void __launch_bounds__(256) norm_rope_store_kernel(const NrsArgs a) {
     const int src_lane = (threadIdx.x & 31) - sl + (rotary ? partner_lane : sl);
 #pragma unroll
     for (int i = 0; i < 4; ++i) other.w[i] = __shfl_sync(0xffffffffu, row.w[i], src_lane);
-    if (kind == 2) continue;
+    if (kind == 2) return;
     if (rotary) {
       float y[8];
       unpack8<T>(other, y);
@@ -199,7 +216,12 @@ __global__ void __launch_bounds__(256) norm_rope_store_kernel(const NrsArgs a) {
       if (kc_off >= 0) *reinterpret_cast<Row8*>((T*)a.kc + kc_off + (int64_t)hh * a.kc_h + e0) = row;
       if (a.k_out) *reinterpret_cast<Row8*>((T*)a.k_out + tok * a.ko_t + (int64_t)hh * a.ko_h + e0) = row;
     }
-  }
+  };
+  // every lane of a warp runs every trip (the shuffles inside are full-warp); lanes past the last head idle as "v"
+#pragma unroll
+  for (int i = 0; i < kPre; ++i)
+    if (i * HSLOTS < total) process(i * HSLOTS, &pre[i]);
+  for (int h0 = kPre * HSLOTS; h0 < total; h0 += HSLOTS) process(h0, nullptr);
 }
 
 }  // namespace mojo
