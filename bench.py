@@ -37,6 +37,8 @@ sys.path.insert(0, ROOT)
 
 CFG2 = dict(batch=64, hq=32, hkv=8, d=128, bs=16, ctx=4096, hidden=4096, inter=12288, eps=1e-6, theta=1e6)
 METRIC = "paged decode-GQA hot-path step throughput (Qwen3-8B-shaped: store+RMSNorm+RoPE+decode+SwiGLU)"
+WORKLOAD = ("cfg2 Qwen3-8B-shaped paged decode layer: batch 64/GPU, 32q/8kv heads, hd 128, page 16, ctx 4096, bf16; "
+            "ResidualAddRMSNorm 64x4096 + RoPE + StorePagedKVCache + PagedDecodeGQA + SwiGLU 64x12288")
 
 
 def load_peaks():
@@ -359,9 +361,7 @@ def run_b200(args):
         "data": "synthetic",
         "impl": "b200",
         "config": {
-            "workload": "cfg2 Qwen3-8B-shaped paged decode layer: batch 64/GPU, 32q/8kv heads, hd 128, page 16, "
-                        "ctx 4096, bf16; ResidualAddRMSNorm 64x4096 + RoPE + StorePagedKVCache + PagedDecodeGQA + "
-                        "SwiGLU 64x12288",
+            "workload": WORKLOAD,
             "batch_per_gpu": B, "ctx": cfg["ctx"], "block_size": cfg["bs"], "parallelism": f"dp{world}",
             "l2": f"inputs larger than L2: {args.layers} rotating KV caches of {2 * B * cfg['ctx'] * cfg['hkv'] * cfg['d'] * 2 / 1e9:.2f} GB",
             "decode_splits": splits,
@@ -485,8 +485,9 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "cfg2 Qwen3-8B-shaped paged decode layer (bounded sample, see cpu_baseline.sample)",
-                   "batch_per_step": B, "ctx": CFG2["ctx"], "block_size": CFG2["bs"]},
+        # the b200 arm's workload; each CPU step is a bounded sample of it (cpu_baseline.sample), tokens/s is per token
+        "config": {"workload": WORKLOAD, "batch_per_gpu": CFG2["batch"], "ctx": CFG2["ctx"], "block_size": CFG2["bs"],
+                   "parallelism": "host cores (rank 0 only)", "sample_batch_per_step": B},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
