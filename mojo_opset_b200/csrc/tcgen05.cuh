@@ -7,10 +7,27 @@
 namespace mojo {
 
 // ---- bounded mbarrier wait: a lost arrive becomes a trap (launch error) instead of a hung GPU ----------
+// The wait SUSPENDS the warp (try_wait with a time hint: resumed as soon as the phase completes, else after the
+// hint) instead of polling: a polling issuer / producer warp takes issue slots from the two softmax warps of its
+// sub-partition - the attention timeline showed the softmax warps next to the QK issuer arriving up to 1000 cycles
+// after their siblings, and a tile only moves on when its slowest warp has arrived.
+constexpr uint32_t kWaitHintNs = 1000000u;
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();  // surfaces as cudaErrorLaunchFailure on the host
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
+        : "memory");
+    if (ok) break;
+    uint64_t now;  // only on the slow path: a wait that outlives 5 s of wall clock is a lost arrive
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    if (now - t0 > 5000000000ull) __trap();  // surfaces as cudaErrorLaunchFailure on the host
   }
 }
 
