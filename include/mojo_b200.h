@@ -163,6 +163,27 @@ MOJO_B200_API int mojo_b200_paged_decode_gqa(
     float softmax_scale, int gqa_interleave, int num_splits, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * MojoPagedDecodeSWA.forward                        mojo_opset/core/operators/attention.py:645-745
+ *
+ * mojo_b200_paged_decode_gqa with the window rule of _generate_window_mask (:507-531) for the single query token at
+ * position seq_len - 1: key k is visible iff k + local_window_size >= position or k < global_window_size (-1 = None).
+ * Only the KV tiles of the global prefix and of the local window are read (O(window) traffic); the splits divide
+ * those.  Built on the tensor-tile kernel (bf16/fp16, head_dim 64/128): other shapes return MOJO_B200_EUNSUPPORTED
+ * (the host mirror then uses mojo_b200_paged_prefill_swa with one query row per sequence).  num_splits and the
+ * workspace: as for mojo_b200_paged_decode_gqa, sized for max_seq_len.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_paged_decode_swa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* total_seq_lens,
+    const int32_t* block_tables, void* out, void* workspace, size_t workspace_bytes,
+    int batch, int num_q_heads, int num_kv_heads, int head_dim, int64_t num_blocks, int block_size,
+    int max_blocks_per_seq, int64_t table_stride, int64_t max_seq_len,
+    int64_t q_stride_b, int64_t q_stride_h, int64_t o_stride_b, int64_t o_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
+    int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t,
+    float softmax_scale, int gqa_interleave, int num_splits, int local_window_size, int global_window_size,
+    int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * MojoPagedPrefillGQA.forward                       mojo_opset/core/operators/attention.py:335-447
  *
  * query [T, Hq, D], cu_q_lens [B+1], cu_total_seq_lens [B+1] or NULL (kv_len = q_len), causal with offset

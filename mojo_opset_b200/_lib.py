@@ -43,6 +43,8 @@ SIGNATURES = {
     "mojo_b200_paged_decode_num_splits": (I, [I, I, I, I, I, L, I]),
     "mojo_b200_paged_decode_workspace_bytes": (Z, [I, I, I, I]),
     "mojo_b200_paged_decode_gqa": (I, [P, P, P, P, P, P, P, Z, I, I, I, I, L, I, I, L, L] + [L] * 10 + [F, I, I, I, P]),
+    "mojo_b200_paged_decode_swa": (I, [P, P, P, P, P, P, P, Z, I, I, I, I, L, I, I, L, L] + [L] * 10
+                                   + [F, I, I, I, I, I, P]),
     "mojo_b200_paged_prefill_gqa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10
                                     + [F, I, I, I, P]),
     "mojo_b200_paged_prefill_swa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10

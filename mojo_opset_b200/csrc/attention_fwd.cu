@@ -469,9 +469,10 @@ static int paged_prefill_impl(
   }
   if (max_q_len <= 0 || max_q_len > total_q_tokens) max_q_len = total_q_tokens;
 
-  if (win_local < 0 && win_global < 0) {  // tcgen05/TMEM kernel when the shape is covered (it has no window mask)
+  {  // tcgen05/TMEM kernel when the shape is covered
     AttnSm100Args a;
     memset(&a, 0, sizeof(a));
+    a.win_local = win_local; a.win_global = win_global;
     a.q = query; a.out = out; a.q_rows = total_q_tokens; a.q_st = q_stride_t; a.q_sh = q_stride_h;
     a.o_st = o_stride_t; a.o_sh = o_stride_h;
     a.k = key_cache; a.v = value_cache; a.k_b = kc_stride_b; a.k_h = kc_stride_h; a.k_t = kc_stride_t;
@@ -568,6 +569,7 @@ extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* va
     a.batch = batch; a.num_q_heads = num_q_heads; a.num_kv_heads = num_kv_heads; a.head_dim = head_dim;
     a.max_q_len = q_len; a.q_len_dense = q_len; a.kv_len_dense = kv_len; a.softmax_scale = softmax_scale;
     a.interleave = 0; a.causal = 0; a.dense = 1; a.round_scores = 0; a.dtype = dtype;
+    a.win_local = a.win_global = -1;
     const int rc = launch_attn_sm100(a, (cudaStream_t)stream);
     if (rc != kAttnNotEligible) return rc;
   }

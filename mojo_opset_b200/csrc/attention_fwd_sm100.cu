@@ -32,6 +32,7 @@
 // remotely on the leader's barriers; commits multicast to both CTAs.
 //
 // FLOPs = 4 * D * (unmasked (q, k) pairs) per query head; the roofline is the bf16 tensor peak.
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +68,9 @@ struct Params {
   int num_q_heads, num_kv_heads, group, interleave, dense;
   int batch, m_blocks;
   int pair_heads;  // PAIR: the two CTAs take two heads of one KV group (else two adjacent query blocks)
+  // sliding window (MojoPagedPrefillSWA, causal only): key visible iff key + win_local >= position or key < win_global;
+  // -1 = not set
+  int win_local, win_global;
   int q_len_dense, kv_len_dense;
   float scale_log2;
   long long* trace;  // developer timeline (MOJO_ATTN_TRACE builds only, tools/attn_trace.py)
@@ -168,6 +172,29 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
     }
     n_t[t] = n;
   }
+  // Sliding window: the KV tiles between the global prefix [0, win_g) and the local window of the CTA's FIRST row are
+  // invisible to every row of the CTA (a later row's window starts later).  They are skipped: from here on n_t[] and
+  // every loop count VISIBLE tiles, and real_tile() maps a visible tile to its place in the sequence.
+  const bool has_win = CAUSAL && (p.win_local >= 0 || p.win_global >= 0);
+  const int win_g = has_win && p.win_global >= 0 ? p.win_global : 0;
+  int win_tg = 0, win_skip = 0;
+  if (has_win) {
+    win_tg = (win_g + kBN - 1) / kBN;
+    if (p.win_local >= 0) {
+      const int t_lo = max(0, off + m0_lead - p.win_local) / kBN;  // tile of the first row's first local key
+      if (t_lo > win_tg) win_skip = t_lo - win_tg;
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (n_t[t] > win_tg) n_t[t] -= win_skip;  // (a tile's causal end always lies past its rows' window start)
+    } else {  // global prefix only
+#pragma unroll
+      for (int t = 0; t < 2; ++t) n_t[t] = min(n_t[t], win_tg);
+    }
+  }
+  auto real_tile = [&](int j) -> int { return j < win_tg ? j : j + win_skip; };
+  auto win_lo = [&](int r) -> int {  // first key of row r's local window
+    return !has_win ? INT_MIN : (p.win_local >= 0 ? off + r - p.win_local : INT_MAX);
+  };
   const int n_max = max(n_t[0], n_t[1]);
   if (n_max == 0) return;  // rows that see no key keep the zeros the output was initialised with
   const int kvh = p.interleave ? hq % p.num_kv_heads : hq / p.group;
@@ -229,7 +256,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           // value columns [64 rank, +64) of V as [128][128 B]
           const int box_rows = is_v ? p.box_rows_v : p.box_rows;
           const int rows = (PAIR && !is_v) ? kBN / 2 : kBN;       // key rows this CTA stages
-          const int tok0 = j * kBN + ((PAIR && !is_v) ? (int)rank * (kBN / 2) : 0);
+          const int tok0 = real_tile(j) * kBN + ((PAIR && !is_v) ? (int)rank * (kBN / 2) : 0);
           const int halves = (PAIR && is_v) ? 1 : 2;              // 64-column halves this CTA stages
           const uint32_t half_bytes = (uint32_t)rows * 128u;
           const uint32_t box_bytes = (uint32_t)box_rows * 128u;   // one half of one box
@@ -386,11 +413,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       const int row = first_row + row_local;  // row inside the sequence
       const int limit = CAUSAL ? min(kv_len - 1, off + row) : kv_len - 1;      // last key this row sees
       const int tile_min_limit = CAUSAL ? min(kv_len - 1, off + first_row) : kv_len - 1;
+      const int row_lo = win_lo(row), tile_max_lo = win_lo(first_row + kBM - 1);  // sliding-window lower bounds
       const float scale_log2 = p.scale_log2;
       float m_ref = -INFINITY, l = 0.f;
 
       for (int j = 0; j < n_tiles; ++j) {
-        const int n0 = j * kBN;
+        const int n0 = real_tile(j) * kBN;
         mbar_wait_bounded(&s_full[t], (uint32_t)j & 1u);
         if ((warp & 3) == 0) TRACE(t, j, 0);
         tc_fence_after();
@@ -430,6 +458,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
 #pragma unroll
           for (int c = 0; c < kBN; ++c)
             if (n0 + c > limit) sr[c] = 0xff800000u;  // -inf
+        }
+        if (has_win && !(n0 >= tile_max_lo || n0 + kBN - 1 < win_g)) {  // a window edge crosses this tile
+#pragma unroll
+          for (int c = 0; c < kBN; ++c)
+            if (n0 + c < row_lo && n0 + c >= win_g) sr[c] = 0xff800000u;  // -inf
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -635,6 +668,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.num_q_heads = a.num_q_heads; p.batch = a.batch;
   // m_blocks counts the grid's steps along the query rows: 256 rows per CTA; a pair of query blocks covers 512
   p.pair_heads = pair_heads ? 1 : 0;
+  p.win_local = a.causal ? a.win_local : -1; p.win_global = a.causal ? a.win_global : -1;
   const int64_t rows_per_step = (pair && !pair_heads) ? 4 * kBM : 2 * kBM;
   p.m_blocks = (int)((a.max_q_len + rows_per_step - 1) / rows_per_step);
   const int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch * ((pair && !pair_heads) ? 2 : 1);

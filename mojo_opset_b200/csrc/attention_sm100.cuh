@@ -29,6 +29,7 @@ struct AttnSm100Args {
   int64_t max_q_len, q_len_dense, kv_len_dense;
   float softmax_scale;
   int interleave, causal, dense, round_scores, dtype;
+  int win_local, win_global;  // sliding window (causal only); -1 = not set
 };
 
 // 0 = launched; kAttnNotEligible = not covered (nothing was launched); anything else = error code.

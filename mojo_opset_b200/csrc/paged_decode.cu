@@ -48,6 +48,9 @@ struct DecodeParams {
   int64_t kc_b, kc_h, kc_t, vc_b, vc_h, vc_t;
   float scale;
   int interleave, num_splits, stages;
+  // MojoPagedDecodeSWA: the query token (position seq_len - 1) sees key k iff k + win_local >= position or
+  // k < win_global; -1 = that window is not set (both -1: every key, MojoPagedDecodeGQA)
+  int win_local, win_global;
 };
 
 __device__ __forceinline__ void split_tile_range(int seq_len, int num_splits, int split, int& tile_begin,
@@ -56,6 +59,41 @@ __device__ __forceinline__ void split_tile_range(int seq_len, int num_splits, in
   const int per = (tiles + num_splits - 1) / num_splits;
   tile_begin = split * per;
   tile_end = min(tiles, tile_begin + per);
+}
+
+// The KV tiles a windowed decode has to read: the tiles of the global prefix [0, g) followed by the tiles of the local
+// window [lo, seq_len).  `visible` tiles are numbered 0 .. n_vis-1 (what the splits divide); tile(v) is the real one.
+// Tiles in between are never loaded, so the traffic is O(window) instead of O(context).
+struct DecodeWindow {
+  int lo, g;        // key k is visible iff k < g or k >= lo (and k < seq_len)
+  int t_g, t_lo;    // visible tile v is real tile v (v < t_g) or t_lo + (v - t_g)
+  int n_vis;
+  __device__ __forceinline__ int tile(int v) const { return v < t_g ? v : t_lo + (v - t_g); }
+  __device__ __forceinline__ bool sees(int key) const { return key < g || key >= lo; }
+};
+__device__ __forceinline__ DecodeWindow decode_window(int seq_len, int win_local, int win_global) {
+  DecodeWindow w;
+  const int tiles = seq_len > 0 ? (seq_len + kTile - 1) / kTile : 0;
+  if (win_local < 0 && win_global < 0) {
+    w.lo = 0; w.g = 0; w.t_g = 0; w.t_lo = 0; w.n_vis = tiles;
+    return w;
+  }
+  w.lo = win_local >= 0 ? max(0, seq_len - 1 - win_local) : seq_len;  // seq_len: no local window at all
+  w.g = win_global >= 0 ? min(win_global, seq_len) : 0;
+  w.t_g = (w.g + kTile - 1) / kTile;
+  w.t_lo = w.lo >= seq_len ? tiles : w.lo / kTile;
+  if (w.t_g >= w.t_lo) {  // the two ranges touch or overlap: every tile (the mask still applies inside a tile)
+    w.t_g = 0; w.t_lo = 0; w.n_vis = tiles;
+  } else {
+    w.n_vis = w.t_g + (tiles - w.t_lo);
+  }
+  return w;
+}
+__device__ __forceinline__ void split_visible_range(const DecodeWindow& w, int num_splits, int split, int& v_begin,
+                                                    int& v_end) {
+  const int per = (w.n_vis + num_splits - 1) / num_splits;
+  v_begin = split * per;
+  v_end = min(w.n_vis, v_begin + per);
 }
 
 __device__ __forceinline__ int q_head_of(const DecodeParams& p, int kvh, int j) {
@@ -91,8 +129,10 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
   const int seq_len = p.seq_lens[b];
   const int rows_valid = min(16, p.group - ht * 16);  // query heads in this tile
 
-  int tile_begin, tile_end;
-  split_tile_range(seq_len, p.num_splits, split, tile_begin, tile_end);
+  const DecodeWindow win = decode_window(seq_len, p.win_local, p.win_global);
+  const bool swa = p.win_local >= 0 || p.win_global >= 0;
+  int tile_begin, tile_end;  // in visible-tile numbering
+  split_visible_range(win, p.num_splits, split, tile_begin, tile_end);
   const int n_tiles = tile_end - tile_begin;
 
   if (n_tiles <= 0) {
@@ -133,7 +173,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
     for (int it = 0; it < n_tiles; ++it) {
       const int stage = it % stages;
       const uint32_t phase = (uint32_t)(it / stages) & 1u;
-      const int tok0 = (tile_begin + it) * kTile;
+      const int tok0 = win.tile(tile_begin + it) * kTile;
       // boxes that hold at least one valid token
       const int want = min(boxes_per_tile, (seq_len - tok0 + box_rows - 1) / box_rows);
       int blk = 0, row_in_page = 0;
@@ -211,7 +251,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
   for (int it = 0; it < n_tiles; ++it) {
     const int stage = it % stages;
     const uint32_t phase = (uint32_t)(it / stages) & 1u;
-    const int tok0 = (tile_begin + it) * kTile;
+    const int tok0 = win.tile(tile_begin + it) * kTile;
     const int valid = seq_len - tok0;  // tokens of this tile that exist (may exceed kTile)
     uint8_t* sk = tiles + (size_t)stage * 2 * TILE_BYTES;
     uint8_t* sv = sk + TILE_BYTES;
@@ -254,8 +294,10 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int tok = warp * 16 + j * 8 + 2 * c + (e & 1);
-        float v = round_through<T>(__fmul_rn(round_through<T>(s[j][e]), scale)) * kLog2e;
-        v = tok < valid ? v : -INFINITY;
+        // MojoPagedDecodeGQA rounds the scores again after scaling (attention.py:217); the SWA op scales in fp32 (:700)
+        const float sc = __fmul_rn(round_through<T>(s[j][e]), scale);
+        float v = (swa ? sc : round_through<T>(sc)) * kLog2e;
+        v = tok < valid && win.sees(tok0 + tok) ? v : -INFINITY;
         s[j][e] = v;
         if (e < 2) tile_lo = fmaxf(tile_lo, v); else tile_hi = fmaxf(tile_hi, v);
       }
@@ -557,13 +599,14 @@ extern "C" size_t mojo_b200_paged_decode_workspace_bytes(int batch, int num_q_he
   return slots * head_dim * sizeof(float) + slots * sizeof(float2) + 256;
 }
 
-extern "C" int mojo_b200_paged_decode_gqa(
+static int paged_decode_impl(
     const void* query, const void* key_cache, const void* value_cache, const int32_t* total_seq_lens,
     const int32_t* block_tables, void* out, void* workspace, size_t workspace_bytes, int batch, int num_q_heads,
     int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq, int64_t table_stride,
     int64_t max_seq_len, int64_t q_stride_b, int64_t q_stride_h, int64_t o_stride_b, int64_t o_stride_h,
     int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t, int64_t vc_stride_b, int64_t vc_stride_h,
-    int64_t vc_stride_t, float softmax_scale, int gqa_interleave, int num_splits, int dtype, void* stream) {
+    int64_t vc_stride_t, float softmax_scale, int gqa_interleave, int num_splits, int win_local, int win_global,
+    int dtype, void* stream) {
   using namespace mojo;
   MOJO_REQUIRE(batch >= 0 && num_q_heads > 0 && num_kv_heads > 0 && head_dim > 0 && block_size > 0 &&
                    max_blocks_per_seq >= 0 && num_blocks >= 0,
@@ -586,6 +629,14 @@ extern "C" int mojo_b200_paged_decode_gqa(
   const bool fast = fast_path_ok(dtype, head_dim, block_size, query, key_cache, value_cache, q_stride_b, q_stride_h,
                                  kc_stride_b, kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t) &&
                     num_blocks > 0 && max_blocks_per_seq > 0;
+  const bool windowed = win_local >= 0 || win_global >= 0;
+  MOJO_REQUIRE(fast || !windowed, MOJO_B200_EUNSUPPORTED,
+               "paged_decode_swa: windows are built on the tensor-tile kernel only (bf16/fp16, head_dim 64/128, "
+               "power-of-two pages, aligned strides)");
+  if (windowed) {  // the splits divide the VISIBLE tiles: size them for the window, not the context
+    const int64_t vis = (win_local >= 0 ? (int64_t)win_local + 1 : 0) + (win_global >= 0 ? win_global : 0) + 2 * kTile;
+    if (vis < max_seq_len) max_seq_len = vis;
+  }
   const int gh = fast ? 16 : (group >= 8 ? 8 : 4);
   const int head_tiles = (group + gh - 1) / gh;
   MOJO_REQUIRE((int64_t)num_kv_heads * head_tiles <= 65535, MOJO_B200_EUNSUPPORTED, "paged_decode: too many heads");
@@ -607,6 +658,7 @@ extern "C" int mojo_b200_paged_decode_gqa(
   p.kc_b = kc_stride_b; p.kc_h = kc_stride_h; p.kc_t = kc_stride_t;
   p.vc_b = vc_stride_b; p.vc_h = vc_stride_h; p.vc_t = vc_stride_t;
   p.scale = softmax_scale; p.interleave = gqa_interleave ? 1 : 0; p.num_splits = num_splits;
+  p.win_local = win_local; p.win_global = win_global;
 
   if (num_splits > 1) {
     const size_t need = mojo_b200_paged_decode_workspace_bytes(batch, num_q_heads, head_dim, num_splits);
@@ -698,4 +750,36 @@ extern "C" int mojo_b200_paged_decode_gqa(
     return check_launch("paged_decode_reduce_kernel");
   }
   return 0;
+}
+
+extern "C" int mojo_b200_paged_decode_gqa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* total_seq_lens,
+    const int32_t* block_tables, void* out, void* workspace, size_t workspace_bytes, int batch, int num_q_heads,
+    int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq, int64_t table_stride,
+    int64_t max_seq_len, int64_t q_stride_b, int64_t q_stride_h, int64_t o_stride_b, int64_t o_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t, int64_t vc_stride_b, int64_t vc_stride_h,
+    int64_t vc_stride_t, float softmax_scale, int gqa_interleave, int num_splits, int dtype, void* stream) {
+  return paged_decode_impl(query, key_cache, value_cache, total_seq_lens, block_tables, out, workspace, workspace_bytes,
+                           batch, num_q_heads, num_kv_heads, head_dim, num_blocks, block_size, max_blocks_per_seq,
+                           table_stride, max_seq_len, q_stride_b, q_stride_h, o_stride_b, o_stride_h, kc_stride_b,
+                           kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t, softmax_scale, gqa_interleave,
+                           num_splits, -1, -1, dtype, stream);
+}
+
+extern "C" int mojo_b200_paged_decode_swa(
+    const void* query, const void* key_cache, const void* value_cache, const int32_t* total_seq_lens,
+    const int32_t* block_tables, void* out, void* workspace, size_t workspace_bytes, int batch, int num_q_heads,
+    int num_kv_heads, int head_dim, int64_t num_blocks, int block_size, int max_blocks_per_seq, int64_t table_stride,
+    int64_t max_seq_len, int64_t q_stride_b, int64_t q_stride_h, int64_t o_stride_b, int64_t o_stride_h,
+    int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t, int64_t vc_stride_b, int64_t vc_stride_h,
+    int64_t vc_stride_t, float softmax_scale, int gqa_interleave, int num_splits, int local_window_size,
+    int global_window_size, int dtype, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(local_window_size >= -1 && global_window_size >= -1, MOJO_B200_EINVAL,
+               "paged_decode_swa: window sizes must be >= 0, or -1 for None");
+  return paged_decode_impl(query, key_cache, value_cache, total_seq_lens, block_tables, out, workspace, workspace_bytes,
+                           batch, num_q_heads, num_kv_heads, head_dim, num_blocks, block_size, max_blocks_per_seq,
+                           table_stride, max_seq_len, q_stride_b, q_stride_h, o_stride_b, o_stride_h, kc_stride_b,
+                           kc_stride_h, kc_stride_t, vc_stride_b, vc_stride_h, vc_stride_t, softmax_scale, gqa_interleave,
+                           num_splits, local_window_size, global_window_size, dtype, stream);
 }

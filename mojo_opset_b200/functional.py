@@ -303,7 +303,11 @@ def paged_decode_gqa(
     gqa_layout: str = "AABB",
     max_total_seq_len: Optional[int] = None,
     num_splits: Optional[int] = None,
+    local_window_size: Optional[int] = None,
+    global_window_size: Optional[int] = None,
 ) -> torch.Tensor:
+    """With a window (``MojoPagedDecodeSWA``) only the KV tiles of the global prefix and of the local window are read;
+    raises ``NotImplementedError`` for shapes the tensor-tile kernel does not cover (``paged_decode_swa`` falls back)."""
     dev = _require_cuda(query, key_cache, value_cache, total_seq_lens, block_tables)
     lib = _lib.load()
     if query.dim() != 3:
@@ -323,19 +327,34 @@ def paged_decode_gqa(
     dt = _lib.dtype_id(query.dtype)
     max_blocks = tables.shape[1]
     hint = max_blocks * block_size if max_total_seq_len is None else min(int(max_total_seq_len), max_blocks * block_size)
+    windowed = local_window_size is not None or global_window_size is not None
+    split_hint = hint
+    if windowed:  # the splits divide the visible tiles (global prefix + local window + their edge tiles)
+        for name, w in (("local_window_size", local_window_size), ("global_window_size", global_window_size)):
+            if w is not None and int(w) < 0:
+                raise ValueError(f"paged_decode_swa: {name} must be >= 0 or None")
+        visible = (0 if local_window_size is None else int(local_window_size) + 1) + int(global_window_size or 0) + 128
+        split_hint = max(1, min(hint, visible))
     if num_splits is None or num_splits <= 0:
         num_splits = lib.mojo_b200_paged_decode_num_splits(batch, num_q_heads, num_kv_heads, head_dim, block_size,
-                                                           hint, dt)
+                                                           split_hint, dt)
     ws_bytes = lib.mojo_b200_paged_decode_workspace_bytes(batch, num_q_heads, head_dim, num_splits)
     workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-    rc = lib.mojo_b200_paged_decode_gqa(
+    common = (
         q.data_ptr(), kc.data_ptr(), vc.data_ptr(), lens.data_ptr(), tables.data_ptr(), out.data_ptr(),
         _lib.ptr(workspace), ws_bytes, batch, num_q_heads, num_kv_heads, head_dim, num_blocks, block_size,
         max_blocks, tables.stride(0) if max_blocks else 0, hint,
         q.stride(0), q.stride(1), out.stride(0), out.stride(1),
         kc.stride(0), kc.stride(1), kc.stride(2), vc.stride(0), vc.stride(1), vc.stride(2),
-        float(softmax_scale), 1 if gqa_layout == "ABAB" else 0, num_splits, dt, _lib.stream_ptr(dev))
-    _lib.check(lib, rc, "paged_decode_gqa")
+        float(softmax_scale), 1 if gqa_layout == "ABAB" else 0, num_splits)
+    if windowed:
+        rc = lib.mojo_b200_paged_decode_swa(
+            *common, -1 if local_window_size is None else int(local_window_size),
+            -1 if global_window_size is None else int(global_window_size), dt, _lib.stream_ptr(dev))
+        _lib.check(lib, rc, "paged_decode_swa")
+    else:
+        rc = lib.mojo_b200_paged_decode_gqa(*common, dt, _lib.stream_ptr(dev))
+        _lib.check(lib, rc, "paged_decode_gqa")
     return out
 
 
@@ -418,11 +437,17 @@ def paged_decode_swa(
     global_window_size: Optional[int] = None,
 ) -> torch.Tensor:
     """``MojoPagedDecodeSWA``: one query token per sequence = the windowed prefill with ``q_len = 1`` rows
-    (``cu_q_lens = 0..B``, cumulative ``total_seq_lens``; both built on the device, no host read).  Without any window
-    this is ``paged_decode_gqa`` (the split-KV streaming kernel)."""
+    (``cu_q_lens = 0..B``, cumulative ``total_seq_lens``; both built on the device, no host read) for shapes outside the
+    tensor-tile decode kernel; inside it, the split-KV streaming kernel reads only the visible KV tiles.  Without any
+    window this is ``paged_decode_gqa``."""
     if local_window_size is None and global_window_size is None:
         return paged_decode_gqa(query, key_cache, value_cache, total_seq_lens, block_tables, softmax_scale, gqa_layout,
                                 max_total_seq_len)
+    try:  # the split-KV decode kernel restricted to the visible KV tiles (bf16/fp16, head_dim 64/128)
+        return paged_decode_gqa(query, key_cache, value_cache, total_seq_lens, block_tables, softmax_scale, gqa_layout,
+                                max_total_seq_len, None, local_window_size, global_window_size)
+    except NotImplementedError:
+        pass  # other shapes: the general attention kernel with one query row per sequence (still CUDA, no fallback)
     dev = _require_cuda(query, key_cache, value_cache, total_seq_lens, block_tables)
     if query.dim() != 3:
         raise ValueError("paged_decode_swa: query must be [batch, num_q_heads, head_dim]")

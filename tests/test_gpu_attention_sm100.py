@@ -119,6 +119,42 @@ def test_sdpa_tcgen05_vs_oracle(F, impl, pair, shape, dtype):
     torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)
 
 
+@pytest.mark.parametrize("local,glob", [(100, None), (700, 130), (None, 300), (4000, 4000), (0, 1), (127, 128)])
+def test_prefill_swa_tcgen05_vs_oracle(F, impl, pair, local, glob):
+    """MojoPagedPrefillSWA on the tcgen05 kernel: window mask on the edge tiles, invisible KV tiles skipped (their
+    pages are poisoned with NaN: they must never be read), ragged batch with cached prefixes."""
+    from oracle import golden
+
+    q_lens, prefix = [900, 260, 1300], [700, 0, 64]
+    Hq, Hkv, bs, dtype = 4, 2, 16, torch.bfloat16
+    q, kc, vc, cu_q, table, cu_kv = _paged_case(q_lens, prefix, Hq, Hkv, bs, dtype, seed=21)
+    ref = golden.paged_prefill_swa(q, kc, vc, cu_q, table, None, cu_kv, "AABB", True, local, glob)
+    impl("tcgen05")
+    out = F.paged_prefill_gqa(q.to(DEV), kc.to(DEV), vc.to(DEV), cu_q.to(DEV), table.to(DEV), None, cu_kv.to(DEV),
+                              "AABB", max(q_lens), max(a + b for a, b in zip(q_lens, prefix)), True, local, glob)
+    torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)
+
+
+def test_prefill_swa_tcgen05_skips_dead_tiles(F, impl, pair):
+    """One 256-row query block late in a long sequence: every KV tile between the global prefix and its window is
+    poisoned with NaN - the kernel must not load it."""
+    from oracle import golden
+
+    Hq, Hkv, bs, dtype, local, glob = 4, 2, 16, torch.bfloat16, 300, 100
+    q, kc, vc, cu_q, table, cu_kv = _paged_case([256], [3000], Hq, Hkv, bs, dtype, seed=22)
+    ref = golden.paged_prefill_swa(q, kc, vc, cu_q, table, None, cu_kv, "AABB", True, local, glob)
+    # rows sit at positions 3000..3255: they see keys < 100 and keys >= 2700.  Tiles 1 .. 20 (keys 128 .. 2687) are dead.
+    dead = table[0, 128 // bs: 2688 // bs].long()
+    kc, vc = kc.clone(), vc.clone()
+    kc[dead] = float("nan")
+    vc[dead] = float("nan")
+    impl("tcgen05")
+    out = F.paged_prefill_gqa(q.to(DEV), kc.to(DEV), vc.to(DEV), cu_q.to(DEV), table.to(DEV), None, cu_kv.to(DEV),
+                              "AABB", 256, 3256, True, local, glob)
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)
+
+
 def _cfg3(T=8192, Hq=32, Hkv=8, D=128, bs=16, seed=3):
     g = torch.Generator(device=DEV).manual_seed(seed)
     nb = T // bs + 10

@@ -4,6 +4,8 @@ atol=rtol=2e-2; fp32 1e-5/1e-5 for decode) and, where the kernel reproduces the 
 much tighter bounds that are asserted as well.
 """
 
+import os
+
 import pytest
 import torch
 
@@ -112,6 +114,58 @@ def test_paged_swa_long_window_skips_tiles(ops):
     out2 = op(_cuda(q), _cuda(kc2), _cuda(vc2), _cuda(cu), _cuda(table))
     assert torch.equal(out2[1000:], out[1000:])
     assert not torch.equal(out2[:900], out[:900])
+
+
+@pytest.mark.parametrize("local,glob", [(100, None), (700, 130), (None, 200), (5000, 5000), (0, 1), (63, 64)])
+@pytest.mark.parametrize("splits", [0, 3])
+def test_paged_decode_swa_long(ops, local, glob, splits):
+    """MojoPagedDecodeSWA on the split-KV decode kernel restricted to the visible KV tiles: contexts of many tiles,
+    windows that leave a gap / touch / cover everything, forced split counts, empty and one-token rows - against the
+    oracle; and the keys outside both windows cannot matter (bit-exact after rewriting them)."""
+    from oracle import golden
+
+    g = torch.Generator().manual_seed(1000 + (local or 0) + 7 * (glob or 0))
+    Hq, Hkv, D, bs = 8, 2, 128, 16
+    lens = [2900, 1, 0, 640, 1337, 64]
+    need = [(n + bs - 1) // bs for n in lens]
+    nb = sum(need) + 3
+    kc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16)
+    vc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16)
+    table = torch.full((len(lens), max(need)), -1, dtype=torch.int32)
+    perm = torch.randperm(nb, generator=g).to(torch.int32)
+    at = 0
+    for i, n in enumerate(need):
+        table[i, :n] = perm[at:at + n]
+        at += n
+    q = torch.randn(len(lens), Hq, D, generator=g).to(torch.bfloat16)
+    seq = torch.tensor(lens, dtype=torch.int32)
+    op = ops.MojoPagedDecodeSWA(global_window_size=glob, local_window_size=local)
+    if splits:
+        os.environ["MOJO_B200_DECODE_SPLITS"] = str(splits)
+    try:
+        out = op(_cuda(q), _cuda(kc), _cuda(vc), _cuda(seq), _cuda(table))
+        ref = golden.paged_decode_swa(q, kc, vc, seq, table, None, "AABB", local, glob)
+        torch.testing.assert_close(out.cpu().float(), ref.float(), atol=2e-2, rtol=2e-2)
+        assert torch.count_nonzero(out[2]).item() == 0
+        # sequence 0 (2900 keys): rewrite the keys strictly between the global prefix and the local window
+        lo = 2899 - local if local is not None else 2900
+        g_end = glob or 0
+        first_page, last_page = (g_end + bs - 1) // bs, lo // bs
+        if last_page - first_page >= 2:
+            mid = table[0, first_page:last_page].long()
+            kc2, vc2 = kc.clone(), vc.clone()
+            kc2[mid] = torch.randn(kc2[mid].shape, generator=g).to(torch.bfloat16)
+            vc2[mid] = torch.randn(vc2[mid].shape, generator=g).to(torch.bfloat16)  # masked in-tile keys: P = 0 exactly
+            # pages of KV tiles (64 keys) that lie entirely outside both windows are never even loaded: poison them
+            t_first, t_last = (g_end + 63) // 64, lo // 64
+            if t_last > t_first:
+                dead = table[0, t_first * 4:t_last * 4].long()
+                kc2[dead] = float("nan")
+                vc2[dead] = float("nan")
+            out2 = op(_cuda(q), _cuda(kc2), _cuda(vc2), _cuda(seq), _cuda(table))
+            assert torch.equal(out2[0], out[0])
+    finally:
+        os.environ.pop("MOJO_B200_DECODE_SPLITS", None)
 
 
 @pytest.mark.parametrize("case", SDPA, ids=_ids(SDPA))
