@@ -41,6 +41,25 @@ WORKLOAD = ("cfg2 Qwen3-8B-shaped paged decode layer: batch 64/GPU, 32q/8kv head
             "ResidualAddRMSNorm 64x4096 + RoPE + StorePagedKVCache + PagedDecodeGQA + SwiGLU 64x12288")
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at communicator
+    creation, for one): point fd 1 at stderr for the duration of the run and keep the real stdout for the line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -383,7 +402,7 @@ def run_b200(args):
         line["extra"] = run_extra(m, dev, peaks)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_batch)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -493,7 +512,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -508,6 +527,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
