@@ -254,10 +254,32 @@ def run_b200(args):
         xs = sorted(xs)
         return xs[len(xs) // 2]
 
+    # The step is launched the way a serving loop launches it: one captured device graph per rotating KV cache
+    # (mojo_opset_b200.runtime.DeviceGraphRunner, mirror of the reference's compile/device_graph.py).  `value` is the
+    # graph-replayed step; the same K steps are ALSO timed launched one by one with CUDA events around every decode
+    # launch - that pass feeds `roofline` and is reported as `eager`.  --eager makes it the `value`.
+    res_graphs = []
+    if not args.eager:
+        for L in range(args.layers):
+            layer_step(res, res_tables[L], res_metas[L], caches[L][0], caches[L][1])  # warm-up outside the capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                layer_step(res, res_tables[L], res_metas[L], caches[L][0], caches[L][1])
+            res_graphs.append(graph)
+        torch.cuda.synchronize()
+
+    def graph_step(i, is_timed):
+        res_graphs[i % args.layers].replay()
+
     with ClockSampler(local_rank) as clocks:
-        resident_samples = []
+        eager_samples = []
         for _ in range(args.repeats):
-            resident_samples.append(timed(resident_step, args.steps, args.warmup))
+            eager_samples.append(timed(resident_step, args.steps, args.warmup))
+        ms_eager = median(eager_samples)
+        resident_samples = eager_samples
+        if not args.eager:
+            resident_samples = [timed(graph_step, args.steps, args.warmup) for _ in range(args.repeats)]
         ms_resident = median(resident_samples)
         # keep the GPU busy long enough for the sampler to see clocks under load on short runs
         extra_rounds = 0
@@ -311,8 +333,12 @@ def run_b200(args):
             dev_packed[j].copy_(host_packed[L], non_blocking=True)
             in_ready[j].record(s_in)
         main.wait_event(in_ready[j])
-        d = dev_views[j]
-        y, _, o, a = layer_step(d, d["table"], d["meta"], caches[L][0], caches[L][1])
+        if e2e_graphs is not None:  # one graph launch instead of five kernel launches from Python
+            graph, (y, _, o, a) = e2e_graphs[(j, L)]
+            graph.replay()
+        else:
+            d = dev_views[j]
+            y, _, o, a = layer_step(d, d["table"], d["meta"], caches[L][0], caches[L][1])
         compute_done[j].record(main)
         out_done[j].synchronize()                       # the caller has read step i-2's results from out_host[j]
         with torch.cuda.stream(s_out):
@@ -321,6 +347,25 @@ def run_b200(args):
                 out_host[j][k].copy_(t, non_blocking=True)
                 t.record_stream(s_out)
             out_done[j].record(s_out)
+
+    # The user-facing way to run a decode step is a captured device graph (mojo_opset_b200.runtime.DeviceGraphRunner,
+    # mirror of the reference's compile/device_graph.py): the five kernels of the layer step are captured once per
+    # (device input buffer, KV cache) pair and replayed.  --e2e-eager launches them one by one from Python instead
+    # (then the host, ~35 us per launch through ctypes, is as slow as the GPU step and the number jitters).
+    e2e_graphs = None
+    if not args.e2e_eager:
+        e2e_graphs = {}
+        for j in range(2):
+            for L in range(args.layers):
+                d = dev_views[j]
+                dev_packed[j].copy_(host_packed[L])
+                layer_step(d, d["table"], d["meta"], caches[L][0], caches[L][1])  # warm-up outside the capture
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = layer_step(d, d["table"], d["meta"], caches[L][0], caches[L][1])
+                e2e_graphs[(j, L)] = (graph, outs)
+        torch.cuda.synchronize()
 
     def e2e_timed(steps, warmup):
         for ev in compute_done + out_done:
@@ -384,10 +429,17 @@ def run_b200(args):
             "batch_per_gpu": B, "ctx": cfg["ctx"], "block_size": cfg["bs"], "parallelism": f"dp{world}",
             "l2": f"inputs larger than L2: {args.layers} rotating KV caches of {2 * B * cfg['ctx'] * cfg['hkv'] * cfg['d'] * 2 / 1e9:.2f} GB",
             "decode_splits": splits,
+            "launch": "eager, one kernel launch at a time" if args.eager else
+                      f"CUDA graph replay, one graph of 5 kernels per rotating KV cache ({args.layers} graphs)",
         },
+        "eager": {"ms_per_step": ms_eager / args.steps, "value": B * world * args.steps / (ms_eager * 1e-3),
+                  "ms_samples": [round(x, 4) for x in eager_samples],
+                  "note": "the same K steps launched one by one from Python with CUDA events around every decode "
+                          "launch: the pass `roofline` is measured in"},
         "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "tokens/s",
                 "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "pipeline": "2-deep: packed pinned H2D | compute | D2H on three streams"},
+                "pipeline": "2-deep: packed pinned H2D | compute | D2H on three streams",
+                "compute_launch": "eager (5 launches per step)" if args.e2e_eager else "CUDA graph replay per step"},
         "gpu_launches": launches_per_step * args.steps,
         "timing": {"repeats": args.repeats, "stat": "median over repeats of a timed region of exactly `steps` steps",
                    "resident_ms_samples": [round(x, 4) for x in resident_samples],
@@ -524,6 +576,8 @@ def main():
     ap.add_argument("--layers", type=int, default=4, help="distinct KV caches rotated across steps")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--e2e-eager", action="store_true", help="e2e leg: launch the step's kernels one by one")
+    ap.add_argument("--eager", action="store_true", help="value = the eagerly launched step instead of graph replay")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
