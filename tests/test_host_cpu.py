@@ -175,3 +175,35 @@ def test_qwen3_patch_swaps_and_reverts():
         if old is not None:
             os.environ["MOJO_BACKEND"] = old
     assert (modeling_qwen3.apply_rotary_pos_emb, modeling_qwen3.Qwen3RMSNorm, modeling_qwen3.Qwen3MLP) == orig
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/mojo_b200.h against its ctypes signature in _lib.SIGNATURES: same number of
+    parameters and the same kind at every position (pointer / int / int64_t / size_t / float) - a marshalling slip
+    (a 64-bit stride passed as a 32-bit int, a swapped pointer) would otherwise only show up as garbage on the GPU."""
+    from mojo_opset_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "mojo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "i64", ctypes.c_float: "f32",
+             ctypes.c_size_t: "size", ctypes.c_char_p: "ptr"}
+
+    def kind_of(param: str) -> str:
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        base = p.rsplit(" ", 1)[0] if " " in p else p
+        base = base.replace("const ", "").strip()
+        return {"int": "int", "int64_t": "i64", "size_t": "size", "float": "f32", "cudaStream_t": "ptr"}[base]
+
+    protos = re.findall(r"MOJO_B200_API\s+([\w\s\*]+?)\b(mojo_b200_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for ret, name, params in protos:
+        params = params.strip()
+        declared = [] if params in ("", "void") else [kind_of(x) for x in params.split(",")]
+        restype, argtypes = _lib.SIGNATURES[name]
+        bound = [kinds[a] if a in kinds else "ptr" for a in argtypes]
+        assert declared == bound, f"{name}: header {declared} != ctypes {bound}"
+        want_ret = "ptr" if "*" in ret else kind_of(ret.strip() + " x")
+        assert kinds.get(restype, "ptr") == want_ret, f"{name}: return type"
