@@ -70,7 +70,7 @@ template <typename T> __device__ __forceinline__ Row8 pack8(const float (&f)[8])
 
 // LPH = lanes per head = D / 8; C = cos/sin element type (float or T); NORM: apply the per-head RMSNorm
 template <typename T, typename C, int LPH, bool NORM>
-__global__ void __launch_bounds__(256) norm_rope_store_kernel(const NrsArgs a) {
+__global__ void __launch_bounds__(256, 5) norm_rope_store_kernel(const NrsArgs a) {
   constexpr int D = LPH * 8;
   constexpr int HSLOTS = 256 / LPH;
   constexpr bool ROUND_T = std::is_same<T, C>::value;  // intermediates of a same-dtype RoPE are rounded to T
