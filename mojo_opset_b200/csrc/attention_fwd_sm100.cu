@@ -599,6 +599,37 @@ static int env_int(const char* name, int fallback) {
   return v && *v ? atoi(v) : fallback;
 }
 
+// Can this device / context co-schedule 2-CTA clusters of the attention CTA (one per SM by shared memory)?  Asked
+// once per device: on a partitioned GPU (MPS limits, green contexts) the answer can be "none", and the launcher then
+// stays with single CTAs instead of failing at launch.
+static bool clusters_fit() {
+  static int cached[64];  // 0 = not asked, 1 = yes, 2 = no
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (cached[dev] == 0) {
+    auto kern = attn_fwd_sm100_kernel<__nv_bfloat16, true, true, 0, true>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // clear: the question failed, the answer is "no"
+      n = 0;
+    }
+    cached[dev] = n > 0 ? 1 : 2;
+  }
+  return cached[dev] == 1;
+}
+
 }  // namespace sm100
 
 int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
@@ -634,7 +665,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   // blocks (no GQA sharing) only pay off once the grid is several waves deep (DiT batch >= 4 of 24 x 4096 x 128)
   const int64_t ctas_single = ((a.max_q_len + 2 * kBM - 1) / (2 * kBM)) * a.num_q_heads * a.batch;
   const int pair_default = pair_heads ? 1 : (ctas_single >= 8 * 148 ? 1 : 0);
-  const bool pair = pair_ok && env_int("MOJO_B200_ATTN_PAIR", pair_default) != 0;
+  const bool pair = pair_ok && env_int("MOJO_B200_ATTN_PAIR", pair_default) != 0 && clusters_fit();
   int box_rows_v = box_rows;
   if (pair) {  // a CTA stages 64 key rows of a K tile and all 128 key rows of one 64-column half of a V tile
     const int64_t bs = a.rows_per_block;
