@@ -12,6 +12,9 @@
 //   math  S = Q K^T (fp32 accumulate) -> [paged prefill: rounded to the input dtype, as the golden's einsum]
 //         -> * scale -> causal / length mask -> online softmax (log2 domain) -> P rounded to the input dtype
 //         -> O += P V (fp32) -> O / l.
+// Sliding windows (MojoPagedPrefillSWA, reference attention.py:533-643; one-row-per-sequence decode fallback): on top
+// of the causal limit a key is visible iff key + local >= position or key < global; KV tiles between the global prefix
+// and the first row's window are skipped by producer and consumers alike.
 // FLOPs = 4 * D * (number of unmasked (q, k) pairs) per query head.
 #include <climits>
 #include <cmath>

@@ -16,6 +16,10 @@
 // Generic path (`paged_decode_simt_kernel`): any dtype (fp32 included), any D <= 256, any page size; one
 // warp per token, dot products by warp shuffle.  Same partial format, same reduce kernel.
 //
+// MojoPagedDecodeSWA (reference attention.py:645-745) is the same kernel over the VISIBLE KV tiles only: the tiles of
+// the global prefix [0, g) followed by the tiles of the local window [len - 1 - local, len); the splits divide that
+// list, the tiles in between are never loaded, and the two edge tiles are masked per key (fast path only).
+//
 // Golden rounding points (reference attention.py:217-228) reproduced: for 16-bit inputs the score is rounded
 // to the input dtype after the dot product and again after scaling; probabilities are rounded to the input
 // dtype before the PV product; everything else is fp32.
