@@ -452,6 +452,14 @@ def run_b200(args):
     }
     if world == 1 and not args.no_extra:
         line["extra"] = run_extra(m, dev, peaks)
+        # the metric names two rooflines: HBM for decode (`roofline`) and the bf16 tensor peak for prefill
+        pf = line["extra"]["prefill_cfg3"]
+        line["roofline_prefill"] = {
+            "kernel": "attn_fwd_sm100_kernel (MojoPagedPrefillGQA, cfg3: T=8192 causal, 32q/8kv, hd 128, page 16)",
+            "bound": "tensor", "achieved": pf["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": pf["frac_of_bf16_peak"], "frac_of_2250_nominal": pf["tflops"] / 2250.0,
+            "peak_source": peaks["source"], "algorithmic_flops": pf["flops"], "us_per_launch": pf["ms"] * 1e3,
+            "traffic": None}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_batch)
     emit(line)
