@@ -24,10 +24,10 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
         : "memory");
     if (ok) break;
-    uint64_t now;  // only on the slow path: a wait that outlives 5 s of wall clock is a lost arrive
+    uint64_t now;  // only on the slow path: a wait that outlives 20 s of wall clock (time-slicing included) is a lost arrive
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     if (t0 == 0) t0 = now;
-    if (now - t0 > 5000000000ull) __trap();  // surfaces as cudaErrorLaunchFailure on the host
+    if (now - t0 > 20000000000ull) __trap();  // surfaces as cudaErrorLaunchFailure on the host
   }
 }
 
