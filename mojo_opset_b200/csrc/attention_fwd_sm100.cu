@@ -502,26 +502,34 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         if ((warp & 3) == 0) TRACE(t, j, 2);
         const float base = m_ref == -INFINITY ? 0.f : m_ref;
         const float2 scale2 = make_float2(scale_log2, scale_log2), nbase2 = make_float2(-base, -base);
+        // eight pairs at a time, stage by stage (scale, exponentials, sums, packs): the softmax warps stall on fixed
+        // instruction latencies (ncu: "wait" is the top stall reason, the pipes are not saturated) and only two of them
+        // share a scheduler, so the independent work has to be laid out inside the warp
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+        float2 sum_c = make_float2(0.f, 0.f), sum_d = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < kBN / 2; ++c) {  // pair c = keys 2c, 2c+1 -> one packed P word
-          float2 x = fma2(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), scale2, nbase2);
-          float2 e;
-#ifdef MOJO_ATTN_DBG_NOEXP  // developer experiment: no exponentials (results garbage)
-          e = x;
-          if (true) {
-          } else if ((c & 3) < EMU) {
-#else
-          if ((c & 3) < EMU) {
-#endif  // this share of the exponentials runs on the FMA pipe instead of the MUFU
-            e = ex2_emulated2(x);
-          } else {
-            e.x = ex2_approx(x.x);
-            e.y = ex2_approx(x.y);
+        for (int c0 = 0; c0 < kBN / 2; c0 += 8) {  // pair c = keys 2c, 2c+1 -> one packed P word
+          float2 x[8], e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            x[i] = fma2(make_float2(__uint_as_float(sr[2 * (c0 + i)]), __uint_as_float(sr[2 * (c0 + i) + 1])), scale2,
+                        nbase2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (((c0 + i) & 3) < EMU) {  // this share of the exponentials runs on the FMA pipe instead of the MUFU
+              e[i] = ex2_emulated2(x[i]);
+            } else {
+              e[i].x = ex2_approx(x[i].x);
+              e[i].y = ex2_approx(x[i].y);
+            }
           }
-          if (c & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
-          sr[c] = pack2<T>(e.x, e.y);  // the packed row reuses the low registers (index c <= 2c)
+          sum_a = add2(sum_a, e[0]); sum_b = add2(sum_b, e[1]); sum_c = add2(sum_c, e[2]); sum_d = add2(sum_d, e[3]);
+          sum_a = add2(sum_a, e[4]); sum_b = add2(sum_b, e[5]); sum_c = add2(sum_c, e[6]); sum_d = add2(sum_d, e[7]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sr[c0 + i] = pack2<T>(e[i].x, e[i].y);  // packed row reuses the low registers
         }
+        sum_a = add2(sum_a, sum_c);
+        sum_b = add2(sum_b, sum_d);
         const float sum0 = sum_a.x + sum_a.y, sum1 = sum_b.x + sum_b.y;
         l += sum0 + sum1;
         if ((warp & 3) == 0) TRACE(t, j, 3);
