@@ -186,6 +186,18 @@ def run_b200(args):
     dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    # N ranks on one box: keep every rank - and the pinned host buffers it is about to allocate (first touch) - on its
+    # GPU's NUMA node, so the e2e leg's H2D / D2H copies do not cross the socket interconnect (MOJO_BENCH_NUMA=0: off)
+    numa = "unbound"
+    if world > 1 and os.environ.get("MOJO_BENCH_NUMA", "1") != "0":
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = f"rank bound to the {len(os.sched_getaffinity(0))} CPUs nearest GPU {local_rank}"
+        except Exception as e:  # noqa: BLE001 - best effort: an unbound rank is still a valid measurement
+            numa = f"unbound ({type(e).__name__})"
 
     os.environ["MOJO_BACKEND"] = "b200"
     import mojo_opset_b200 as m
@@ -429,6 +441,7 @@ def run_b200(args):
             "batch_per_gpu": B, "ctx": cfg["ctx"], "block_size": cfg["bs"], "parallelism": f"dp{world}",
             "l2": f"inputs larger than L2: {args.layers} rotating KV caches of {2 * B * cfg['ctx'] * cfg['hkv'] * cfg['d'] * 2 / 1e9:.2f} GB",
             "decode_splits": splits,
+            "host_affinity": numa,
             "launch": "eager, one kernel launch at a time" if args.eager else
                       f"CUDA graph replay, one graph of 5 kernels per rotating KV cache ({args.layers} graphs)",
         },
