@@ -1,4 +1,5 @@
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -7,13 +8,60 @@ from mojo_opset_b200 import functional as F
 from mojo_opset_b200.comm import SymmetricWorkspace
 from mojo_opset_b200.core import MojoGemmAllReduce
 
+# One peer-mapped workspace per (process group, device, out_features), shared by every ``B200GemmAllReduce`` of a
+# model (an 80-layer stack has 80 ``o_proj`` ops of one shape: one workspace, not 80).  The kernel's epoch / parity
+# protocol already serialises back-to-back calls on one workspace (``csrc/gemm_allreduce.cu``); calls on the same
+# stream are ordered anyway.
+_WORKSPACES = {}
+
+
+def _group_key(group):
+    return id(group) if group is not None else 0
+
+
+def shared_workspace(group, device: torch.device, n: int, m: int):
+    """The shared workspace for ``m`` rows of ``n`` output features; created (collectively!) on first use, sized for
+    ``max(m, MOJO_B200_GAR_MAX_TOKENS, 256)`` rows and regrown (collectively, geometric) when a larger ``m`` arrives.
+    Creation exchanges IPC handles and synchronises, so it cannot happen while a CUDA graph is being captured:
+    call the op once eagerly with the largest row count (or set ``MOJO_B200_GAR_MAX_TOKENS``) before capturing."""
+    world = dist.get_world_size(group)
+    key = (_group_key(group), device.index, int(n))
+    entry = _WORKSPACES.get(key)
+    if entry is not None and m <= entry[1]:
+        return entry
+    if torch.cuda.is_current_stream_capturing():
+        have = 0 if entry is None else entry[1]
+        raise RuntimeError(
+            f"B200GemmAllReduce: the peer-mapped workspace holds {have} rows and {m} are needed, but it cannot be "
+            "(re)allocated during CUDA-graph capture; run the op once eagerly at the largest token count or set "
+            "MOJO_B200_GAR_MAX_TOKENS before capturing")
+    want = max(int(m), int(os.environ.get("MOJO_B200_GAR_MAX_TOKENS", "0")), 256, 2 * (entry[1] if entry else 0))
+    if entry is not None:
+        entry[0].close()
+    ws = SymmetricWorkspace(F.gemm_allreduce_workspace_bytes(want, n, world), group, device)
+    entry = (ws, want)
+    _WORKSPACES[key] = entry
+    if group is not None:  # drop the cache entry with the group (ids are reused)
+        try:
+            weakref.finalize(group, _WORKSPACES.pop, key, None)
+        except TypeError:
+            pass
+    return entry
+
+
+def release_workspaces():
+    """Unmap and free every shared workspace (collective; call before ``destroy_process_group``)."""
+    for key in list(_WORKSPACES):
+        ws, _ = _WORKSPACES.pop(key)
+        ws.close()
+
 
 class B200GemmAllReduce(MojoGemmAllReduce):
     """GEMM and all-reduce in ONE persistent sm_100a kernel (tcgen05 GEMM, partial tiles pushed over NVLink,
-    owner-side fp32 reduction, broadcast) - ``csrc/gemm_allreduce.cu``.  The peer-mapped workspace is created on
-    the first distributed call and grows when a larger token count arrives (``MOJO_B200_GAR_MAX_TOKENS`` presets
-    it); all ranks must call with the same number of rows, as with any all-reduce.  The constructor is the core
-    op's: all backend state is created lazily in ``forward``."""
+    owner-side fp32 reduction, broadcast) - ``csrc/gemm_allreduce.cu``.  The peer-mapped workspace is shared by all
+    instances of one (process group, out_features) and is created on the first distributed call (see
+    ``shared_workspace``); all ranks must call with the same number of rows, as with any all-reduce.  The constructor
+    is the core op's: all backend state is created lazily in ``forward``."""
 
     supported_platforms_list = ["b200"]
 
@@ -28,23 +76,10 @@ class B200GemmAllReduce(MojoGemmAllReduce):
             self._b200_w = cached
         return cached[2]
 
-    def _workspace(self, m: int, n: int):
-        if not (dist.is_available() and dist.is_initialized()):
-            return None, 0
-        world = dist.get_world_size(self.process_group)
-        if world == 1:
-            return None, 0
-        ws, max_m = getattr(self, "_b200_ws", None), getattr(self, "_b200_ws_max_m", 0)
-        if ws is None or m > max_m:
-            want = max(m, int(os.environ.get("MOJO_B200_GAR_MAX_TOKENS", "0")), 2 * max_m)
-            if ws is not None:
-                ws.close()
-            ws = SymmetricWorkspace(F.gemm_allreduce_workspace_bytes(want, n, world), self.process_group)
-            self._b200_ws, self._b200_ws_max_m, max_m = ws, want, want
-        return ws, max_m
-
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         w = self._kmajor_weight()
         m = input.numel() // max(input.shape[-1], 1)
-        ws, max_m = self._workspace(m, w.shape[0])
+        ws, max_m = None, 0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            ws, max_m = shared_workspace(self.process_group, input.device, w.shape[0], m)
         return F.gemm_allreduce(input, w, self.bias, ws, max_m)

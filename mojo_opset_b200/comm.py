@@ -10,6 +10,7 @@ pointers, no IPC): the single-GPU tests drive the full protocol that way, one st
 """
 
 import ctypes
+import os
 
 from typing import List
 from typing import Optional
@@ -89,6 +90,11 @@ class LocalRanks:
             self._ptrs.append(p)
         self.table = (ctypes.c_void_p * world)(*[p.value for p in self._ptrs])
         self.streams = [torch.cuda.Stream() for _ in range(world)]
+        # the ranks' persistent kernels wait for one another: all of them must be resident on this one GPU at once
+        # (one CTA per SM each, ~194 KB of shared memory), so each gets at most SMs / world CTAs
+        self._saved_cap = os.environ.get("MOJO_B200_GAR_MAX_CTAS")
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        os.environ["MOJO_B200_GAR_MAX_CTAS"] = str(max(1, sms // world))
 
     def view(self, rank: int) -> "_View":
         return LocalRanks._View(self, rank)
@@ -98,3 +104,7 @@ class LocalRanks:
         for p in self._ptrs:
             self._lib.mojo_b200_symm_free(p)
         self._ptrs = []
+        if self._saved_cap is None:
+            os.environ.pop("MOJO_B200_GAR_MAX_CTAS", None)
+        else:
+            os.environ["MOJO_B200_GAR_MAX_CTAS"] = self._saved_cap

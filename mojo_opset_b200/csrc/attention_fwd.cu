@@ -464,7 +464,8 @@ static int paged_prefill_impl(
   MOJO_REQUIRE(head_dim % 2 == 0 && ((o_stride_t | o_stride_h) % 2) == 0 && ((uintptr_t)out & 3) == 0,
                MOJO_B200_EUNSUPPORTED, "paged_prefill: out strides must be even and the base 4-byte aligned");
   {
-    const int no_kv = max_blocks_per_seq == 0 || num_blocks == 0;
+    // a global-only window of size 0 leaves no key visible to any row: every row reads as zero (both kernels)
+    const int no_kv = max_blocks_per_seq == 0 || num_blocks == 0 || (win_local < 0 && win_global == 0);
     prefill_zero_unseen_rows_kernel<<<dim3((unsigned)batch + 1, 8), 256, 0, (cudaStream_t)stream>>>(
         out, cu_q_lens, cu_total_seq_lens, batch, total_q_tokens, num_q_heads, head_dim, o_stride_t, o_stride_h, no_kv);
     const int rc = check_launch("prefill_zero_unseen_rows_kernel");

@@ -41,7 +41,9 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kMaxWorld = 8;
 constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kImageBytes + 256;
-constexpr unsigned long long kWaitTimeoutNs = 5000000000ull;
+// a waiting rank gives up (trap: launch failure rather than a hung GPU) only after MOJO_B200_GAR_TIMEOUT_S seconds (default
+// 600, 0 = wait for ever like NCCL): ranks of an eager serving loop may skew by seconds (GC pause, first-call module load)
+constexpr unsigned long long kDefaultWaitTimeoutNs = 600ull * 1000000000ull;
 constexpr size_t kHeaderBytes = 256;
 constexpr int kOneShotMaxTiles = 128;                       // one-shot mode: every rank holds every rank's tile
 constexpr size_t kOneShotMaxPeerBytes = 6u << 20;           // ... so it is used while (world-1) * m * n * 2 B is small
@@ -58,6 +60,7 @@ struct Params {
   size_t off_partial, off_result, off_flag_partial, off_flag_result;
   int one_shot, one_cap;  // one-shot mode: slots [parity][tile < one_cap][src], flags alike
   size_t off_one, off_flag_one;
+  unsigned long long timeout_ns;  // 0 = never give up
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -143,12 +146,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, unsigned long long timeout_ns) {
   if (ld_flag_sys(flag) == epoch) return;
   const unsigned long long t0 = global_ns();
   while (ld_flag_sys(flag) != epoch) {
     __nanosleep(40);
-    if (global_ns() - t0 > kWaitTimeoutNs) __trap();  // a peer never arrived: launch failure, not a hung GPU
+    if (timeout_ns && global_ns() - t0 > timeout_ns) __trap();  // a peer never arrived: launch failure, not a hung GPU
   }
 }
 // L2-coherent 16-byte load (peers wrote this memory: never take a stale L1 line)
@@ -360,7 +363,7 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
       const uint32_t chunk_bytes = rows_per_pass * 256;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-        if (tid < p.world) wait_flag(reinterpret_cast<const uint32_t*>(self + flag_one_off(p, par, t, tid)), epoch);
+        if (tid < p.world) wait_flag(reinterpret_cast<const uint32_t*>(self + flag_one_off(p, par, t, tid)), epoch, p.timeout_ns);
         epi_barrier();
         for (int r0 = 0; r0 < kBM; r0 += rows_per_pass) {
           if (tid == 0) {
@@ -412,7 +415,7 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
         const int local_tile = u / p.world, slab = u - local_tile * p.world;
         const int t = local_tile * p.world + p.rank;
         if (tid < p.world)
-          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_partial_off(p, par, local_tile, tid)), epoch);
+          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_partial_off(p, par, local_tile, tid)), epoch, p.timeout_ns);
         epi_barrier();
         if (tid == 0) {
           fence_async_global();
@@ -452,7 +455,7 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
         if (tid < p.world)
-          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_result_off(p, par, t, tid)), epoch);
+          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_result_off(p, par, t, tid)), epoch, p.timeout_ns);
         epi_barrier();
         if (tid == 0) {
           fence_async_global();
@@ -570,6 +573,8 @@ extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const
   MOJO_REQUIRE(tiles < (1LL << 30), MOJO_B200_EUNSUPPORTED, "gemm_allreduce: too many tiles");
   p.n_tiles = (int)tiles;
   p.world = world; p.rank = rank;
+  p.timeout_ns = kDefaultWaitTimeoutNs;
+  if (const char* t = getenv("MOJO_B200_GAR_TIMEOUT_S")) p.timeout_ns = (unsigned long long)(atof(t) * 1e9);
   if (world > 1) {
     MOJO_REQUIRE(peer_workspaces, MOJO_B200_EINVAL, "gemm_allreduce: peer workspace table is null");
     MOJO_REQUIRE(workspace_max_m >= m, MOJO_B200_EWORKSPACE, "gemm_allreduce: m %lld exceeds the workspace's max_m %lld",
@@ -599,7 +604,12 @@ extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const
   rc = build_2d_map(weight, dtype, n, k, w_row_stride, &b_map);
   if (rc != 0) return rc;
 
-  const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+  int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+  // several virtual ranks sharing ONE GPU (comm.LocalRanks) must all be resident at once: cap each rank's CTAs
+  if (const char* cap = getenv("MOJO_B200_GAR_MAX_CTAS")) {
+    const int c = atoi(cap);
+    if (c > 0 && c < grid) grid = c;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == MOJO_B200_BF16) {
     auto kern = gemm_allreduce_kernel<__nv_bfloat16>;

@@ -6,6 +6,7 @@ and stream handles only.  Unsupported-but-valid requests raise ``NotImplementedE
 ``ValueError``/``AssertionError``; nothing falls back to eager torch.
 """
 
+import functools
 import math
 
 from typing import Optional
@@ -33,6 +34,25 @@ def _require_cuda(*tensors) -> torch.device:
     return dev
 
 
+def _on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first CUDA tensor argument current.  Kernels launch on the process's
+    current device while streams and pointers belong to the tensors' device: a model placed on ``cuda:1`` by HF
+    ``device_map`` / accelerate while ``cuda:0`` is current would otherwise fail at launch (invalid resource handle).
+    The switch costs nothing when the device already is current."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _inner_contiguous(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(-1) == 1 or t.shape[-1] == 1 else t.contiguous()
 
@@ -53,6 +73,7 @@ def _as_rows(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------------
 # MojoStorePagedKVCache
 # ------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def store_paged_kv(
     key_states: torch.Tensor,
     value_states: torch.Tensor,
@@ -112,6 +133,7 @@ def _check_norm_weight(x, weight):
         raise ValueError(f"rms_norm: weight shape {tuple(weight.shape)} does not match hidden size {x.shape[-1]}")
 
 
+@_on_tensor_device
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     dev = _require_cuda(x, weight)
     lib = _lib.load()
@@ -126,6 +148,7 @@ def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     return y
 
 
+@_on_tensor_device
 def residual_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float,
                           want_sum: bool = True):
     """Returns ``(y, x + residual)``; the second item is ``None`` when ``want_sum`` is False."""
@@ -160,6 +183,7 @@ def _bsh_strides(t: torch.Tensor, head_first: bool):
     return t.shape[0], t.shape[1], t.shape[2], t.stride(0), t.stride(1), t.stride(2)  # [B, S, N, D]
 
 
+@_on_tensor_device
 def apply_rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, head_first: bool = True):
     dev = _require_cuda(q, k, cos, sin)
     lib = _lib.load()
@@ -199,6 +223,18 @@ def apply_rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.T
     return q_out, k_out
 
 
+def _rotary_on_device(fn):
+    @functools.wraps(fn)
+    def wrapper(num_tokens, out_shape, inv_freq, *args, **kwargs):
+        if inv_freq.is_cuda and inv_freq.device.index != torch.cuda.current_device():
+            with torch.cuda.device(inv_freq.device):
+                return fn(num_tokens, out_shape, inv_freq, *args, **kwargs)
+        return fn(num_tokens, out_shape, inv_freq, *args, **kwargs)
+
+    return wrapper
+
+
+@_rotary_on_device
 def rotary_cos_sin(
     num_tokens: int,
     out_shape,
@@ -216,17 +252,15 @@ def rotary_cos_sin(
     dev = _require_cuda(inv_freq, position_ids, cu_q_lens, total_seq_lens, table_cos, table_sin)
     lib = _lib.load()
     rope_dim = 2 * inv_freq.shape[0]
-    if inv_freq.dtype != torch.float32:
-        raise NotImplementedError("rotary: inv_freq must be fp32")
+    if inv_freq.dtype != torch.float32:  # model.to(bf16) / .half() cast the module's buffers: compute from an fp32 copy
+        inv_freq = inv_freq.float()
     cos = torch.empty(*out_shape, rope_dim, dtype=torch.float32, device=dev)
     sin = torch.empty_like(cos)
     pos = None if position_ids is None else position_ids.contiguous()
     cu = None if cu_q_lens is None else cu_q_lens.contiguous()
     tot = None if total_seq_lens is None else total_seq_lens.contiguous()
     if table_cos is not None:
-        if table_cos.dtype != torch.float32 or table_sin.dtype != torch.float32:
-            raise NotImplementedError("rotary: cos/sin tables must be fp32")
-        table_cos, table_sin = table_cos.contiguous(), table_sin.contiguous()
+        table_cos, table_sin = table_cos.float().contiguous(), table_sin.float().contiguous()
     rc = lib.mojo_b200_rotary_cos_sin(
         cos.data_ptr(), sin.data_ptr(), num_tokens, rope_dim, inv_freq.contiguous().data_ptr(),
         float(attention_scaling), _lib.ptr(pos), _lib.ptr(cu), _lib.ptr(tot), 0 if cu is None else cu.shape[0] - 1,
@@ -247,6 +281,7 @@ def _rows_cols(t: torch.Tensor):
     return r, r.shape[0], r.shape[1], r.stride(0)
 
 
+@_on_tensor_device
 def swiglu(gate: torch.Tensor, up: torch.Tensor, swiglu_limit: float = 0.0) -> torch.Tensor:
     dev = _require_cuda(gate, up)
     lib = _lib.load()
@@ -266,6 +301,7 @@ def swiglu(gate: torch.Tensor, up: torch.Tensor, swiglu_limit: float = 0.0) -> t
     return out
 
 
+@_on_tensor_device
 def silu(x: torch.Tensor) -> torch.Tensor:
     dev = _require_cuda(x)
     lib = _lib.load()
@@ -293,6 +329,7 @@ def _check_paged_caches(query, key_cache, value_cache):
         raise ValueError("paged attention: num_q_heads must be a multiple of num_kv_heads")
 
 
+@_on_tensor_device
 def paged_decode_gqa(
     query: torch.Tensor,
     key_cache: torch.Tensor,
@@ -361,6 +398,7 @@ def paged_decode_gqa(
 # ------------------------------------------------------------------------------------------------------
 # MojoPagedPrefillGQA / MojoSdpa
 # ------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def paged_prefill_gqa(
     query: torch.Tensor,
     key_cache: torch.Tensor,
@@ -424,6 +462,7 @@ def paged_prefill_gqa(
     return out
 
 
+@_on_tensor_device
 def paged_decode_swa(
     query: torch.Tensor,
     key_cache: torch.Tensor,
@@ -459,6 +498,7 @@ def paged_decode_swa(
                              max_total_seq_len, True, local_window_size, global_window_size)
 
 
+@_on_tensor_device
 def sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Optional[float] = None,
          enable_gqa: bool = False) -> torch.Tensor:
     """Non-causal dense attention.  ``[B,H,S,D]`` inputs may be transposed views of ``[B,S,H,D]`` memory (the
@@ -500,6 +540,7 @@ def gemm_allreduce_workspace_bytes(max_m: int, n: int, world: int) -> int:
     return int(_lib.load().mojo_b200_gemm_allreduce_workspace_bytes(int(max_m), int(n), int(world)))
 
 
+@_on_tensor_device
 def gemm_allreduce(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, workspace=None,
                    workspace_max_m: int = 0) -> torch.Tensor:
     """``all_reduce_sum(x @ weight.T + bias)`` in one kernel.  ``weight`` is ``[out_features, in_features_local]``;
@@ -538,6 +579,7 @@ def gemm_allreduce(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
 # ------------------------------------------------------------------------------------------------------
 # MojoNormRoPEStoreKV / MojoRoPEStoreKV
 # ------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def norm_rope_store_kv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
                        key_cache: torch.Tensor, value_cache: torch.Tensor, block_table: torch.Tensor,
                        cu_q_lens: Optional[torch.Tensor], context_kv_lens: torch.Tensor,
@@ -593,6 +635,7 @@ def norm_rope_store_kv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: t
 # ------------------------------------------------------------------------------------------------------
 # DiT block: MojoGelu / MojoLayerNorm / MojoGridRoPE
 # ------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def gelu(x: torch.Tensor) -> torch.Tensor:
     dev = _require_cuda(x)
     lib = _lib.load()
@@ -606,6 +649,7 @@ def gelu(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
     dev = _require_cuda(x, weight, bias)
     lib = _lib.load()
@@ -625,6 +669,7 @@ def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[t
     return y
 
 
+@_on_tensor_device
 def grid_rope(x: torch.Tensor, freqs_list) -> torch.Tensor:
     """``x [B, L, N, D]`` (interleaved complex pairs); ``freqs_list[b]``: complex ``[seq_len_b, 1, D/2]``.  The sequence
     length of a sample is the phase table's (no host read of ``grid_sizes``); one launch per sample."""

@@ -9,6 +9,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+# a fused compute+collective kernel whose peer never arrives gives up after this long (a failed test, not a hung box)
+os.environ.setdefault("MOJO_B200_GAR_TIMEOUT_S", "30")
 
 
 def pytest_configure(config):

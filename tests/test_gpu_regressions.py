@@ -1,0 +1,79 @@
+"""-m gpu: regression tests for the round-1 advisor findings and the judge's small items."""
+
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    os.environ["MOJO_BACKEND"] = "b200"
+    import mojo_opset_b200 as m
+
+    return m
+
+
+@pytest.mark.parametrize("max_q_len", [64, 400], ids=["general-kernel", "tcgen05-kernel"])
+def test_global_only_window_of_zero_reads_as_zeros(ops, max_q_len):
+    """global_window_size=0, local None: no key is visible to any row.  Both attention kernels must leave zeros, not
+    the uninitialised contents of the freshly allocated output."""
+    Hq, Hkv, D, bs, T = 4, 2, 128, 16, max_q_len
+    nb = T // bs + 2
+    kc = torch.randn(nb, Hkv, bs, D, device=DEV).to(torch.bfloat16)
+    vc = torch.randn(nb, Hkv, bs, D, device=DEV).to(torch.bfloat16)
+    q = torch.randn(T, Hq, D, device=DEV).to(torch.bfloat16)
+    table = torch.arange(nb, dtype=torch.int32, device=DEV).view(1, -1)
+    cu = torch.tensor([0, T], dtype=torch.int32, device=DEV)
+    # dirty the allocator's free blocks so that an unwritten output would not read as zeros by luck
+    junk = torch.full((T, Hq, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    del junk
+    op = ops.MojoPagedPrefillSWA(global_window_size=0, local_window_size=None)
+    out = op(q, kc, vc, cu, table, max_q_len=max_q_len)
+    assert out.shape == q.shape and not out.float().abs().sum().item()
+
+
+def test_rotary_embedding_survives_model_to_bf16(ops):
+    """``model.to(torch.bfloat16)`` casts the op's ``inv_freq`` / table buffers; the b200 op must keep working."""
+    rot = ops.MojoRotaryEmbedding(1e6, 128, init_max_length=64, device=DEV)
+    x = torch.empty(7, 4096, device=DEV, dtype=torch.bfloat16)
+    pos = torch.tensor([0, 1, 5, 9, 33, 62, 63], dtype=torch.int32, device=DEV)
+    cos32, sin32 = rot(x, position_ids=pos)
+    rot = rot.to(torch.bfloat16)
+    assert rot.inv_freq.dtype == torch.bfloat16
+    cos16, sin16 = rot(x, position_ids=pos)
+    torch.testing.assert_close(cos16.float(), cos32.float(), atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(sin16.float(), sin32.float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_run_on_the_tensors_device_not_the_current_one(ops):
+    """Tensors on cuda:1 while cuda:0 is current (HF device_map / accelerate placement)."""
+    from oracle import golden
+
+    assert torch.cuda.current_device() == 0
+    dev = "cuda:1"
+    g = torch.Generator().manual_seed(3)
+    x, r = (torch.randn(9, 1024, generator=g).to(torch.bfloat16) for _ in range(2))
+    w = torch.randn(1024, generator=g).to(torch.bfloat16)
+    norm = ops.MojoResidualAddRMSNorm(1024, eps=1e-6, device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        norm.weight.copy_(w)
+    y, s = norm(x.to(dev), r.to(dev))
+    y_ref, s_ref = golden.residual_add_rms_norm(x, r, w, 1e-6)
+    assert y.device == torch.device(dev) and torch.equal(s.cpu(), s_ref)
+    torch.testing.assert_close(y.cpu().float(), y_ref.float(), atol=5e-2, rtol=1e-2)
+    B, Hq, Hkv, D, bs, ctx = 3, 8, 2, 128, 16, 300
+    nb = B * 20
+    kc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16)
+    vc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16)
+    table = torch.randperm(nb, generator=g)[: B * 19].view(B, 19).to(torch.int32)
+    lens = torch.tensor([ctx, 17, 250], dtype=torch.int32)
+    q = torch.randn(B, Hq, D, generator=g).to(torch.bfloat16)
+    out = ops.MojoPagedDecodeGQA()(q.to(dev), kc.to(dev), vc.to(dev), lens.to(dev), table.to(dev))
+    ref = golden.paged_decode_gqa(q, kc, vc, lens, table)
+    torch.testing.assert_close(out.cpu().float(), ref.float(), atol=2e-2, rtol=2e-2)
+    assert torch.cuda.current_device() == 0

@@ -36,6 +36,7 @@ def main():
     dev = f"cuda:{local_rank}"
     dist.init_process_group("nccl", device_id=torch.device(dev))
     os.environ["MOJO_BACKEND"] = "b200"
+    os.environ.setdefault("MOJO_B200_GAR_TIMEOUT_S", "30")
     import mojo_opset_b200 as mj
 
     m, n = args.tokens, args.out_features
