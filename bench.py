@@ -767,11 +767,16 @@ def run_tp_cfg4(m, dev, rank, world, peaks, args, barrier, max_over_ranks):
         return graph.replay
 
     K, W = args.steps, args.warmup
-    g_fused, g_nocomm, g_attn = graphed(step_fused), graphed(step_nocomm), graphed(attn)
-    ms_fused = median([timed_loop(g_fused, K, W) for _ in range(3)])
-    ms_nocomm = median([timed_loop(g_nocomm, K, W) for _ in range(3)])
-    ms_attn = median([timed_loop(g_attn, K, W) for _ in range(3)])
-    ms_unfused = median([timed_loop(step_unfused, K, W) for _ in range(3)])      # NCCL launched eagerly
+    # the four variants are timed INTERLEAVED (fused, no-collective, attention only, cuBLAS + NCCL; five rounds, median
+    # per variant): the differences between them are tens of microseconds of a multi-millisecond step, less than the
+    # drift of a GPU warming up over back-to-back regions of one variant each
+    variants = {"fused": graphed(step_fused), "nocomm": graphed(step_nocomm), "attn": graphed(attn),
+                "unfused": step_unfused}      # NCCL launched eagerly
+    samples = {name: [] for name in variants}
+    for _ in range(5):
+        for name, fn in variants.items():
+            samples[name].append(timed_loop(fn, K, W if not samples[name] else 2))
+    ms_fused, ms_nocomm, ms_attn, ms_unfused = (median(samples[n]) for n in ("fused", "nocomm", "attn", "unfused"))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
 
     def attn_timed_once(i):
@@ -803,7 +808,8 @@ def run_tp_cfg4(m, dev, rank, world, peaks, args, barrier, max_over_ranks):
         "allreduce_bytes": B * hidden * 2,
         "parity": {"ok": ok, "decode_rel_err_vs_oracle": err_o, "fused_rel_err_vs_oracle": err_y,
                    "fused_rel_tol": tol, "decode_rel_tol": 1.5e-2, "ranks_bit_identical": same, "notes": notes},
-        "timing": "CUDA events, median of 3 regions of K steps, max over ranks",
+        "timing": "CUDA events, the four variants interleaved, median of 5 regions of K steps each, max over ranks",
+        "ms_samples": {k: [round(x, 4) for x in v] for k, v in samples.items()},
     }
     return leg, ok
 
