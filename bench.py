@@ -600,6 +600,28 @@ def _time_gpu(fn, iters, warmup=3):
     return a.elapsed_time(b) / iters
 
 
+def _time_gpu_burst(fn, iters=10, ramp_ms=30.0):
+    """Burst timing of ONE kernel the way MEASURED_PEAKS.json takes its burst figures: the GPU is first brought out
+    of its idle clocks with `ramp_ms` of the same work, then `iters` back-to-back launches are timed one by one with
+    CUDA events; returns (median, best) in ms."""
+    fn()
+    torch.cuda.synchronize()
+    time.sleep(0.5)  # let the power / thermal state of whatever ran before decay: this is the kernel "timed alone"
+    t0 = time.perf_counter()
+    while (time.perf_counter() - t0) * 1e3 < ramp_ms:
+        for _ in range(4):
+            fn()
+        torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    evs[0].record()
+    for i in range(iters):
+        fn()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    times = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
+    return times[len(times) // 2], times[0]
+
+
 def run_extra(m, dev, peaks, args):
     """cfg3 (prefill 8192, causal; burst of 10 launches and a >= 2 s sustained loop) and cfg5 (DiT SDPA: one GPU's
     share at 8 GPUs = 2 of 16 batch elements, and the whole batch)."""
@@ -614,30 +636,33 @@ def run_extra(m, dev, peaks, args):
     cu = torch.tensor([0, T], dtype=torch.int32, device=dev)
     prefill = m.MojoPagedPrefillGQA()
     run_prefill = lambda: prefill(q, kc, vc, cu, table, max_q_len=T, max_total_seq_len=T)  # noqa: E731
-    ms = _time_gpu(run_prefill, 10)
+    ms, ms_best = _time_gpu_burst(run_prefill)
     flops = 4 * Hq * D * (T * (T + 1) // 2)
     out["prefill_cfg3"] = {"workload": "MojoPagedPrefillGQA T=8192 causal 32q/8kv hd128 page16 bf16", "ms": ms,
+                           "ms_best": ms_best, "tflops_best": flops / ms_best / 1e9,
+                           "timing": "30 ms ramp out of idle clocks, then 10 launches timed one by one: median (best)",
                            "tflops": flops / ms / 1e9, "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"],
                            "tokens_per_s": T / (ms * 1e-3), "flops": flops}
-    if args.sustain_s > 0:
-        iters = max(10, int(2.0 * args.sustain_s * 1e3 / ms))
-        ms_s = _time_gpu(run_prefill, iters, warmup=1)
-        sus_peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
-        out["prefill_cfg3"]["sustained"] = {"seconds": ms_s * iters * 1e-3, "launches": iters, "ms": ms_s,
-                                            "tflops": flops / ms_s / 1e9, "peak_sustained": sus_peak,
-                                            "frac_of_bf16_sustained_peak": flops / ms_s / 1e9 / sus_peak}
     H, S = CFG5["heads"], CFG5["seq"]
     sdpa = m.MojoSdpa()
     for key, Bd, note in (("sdpa_cfg5_per_gpu", 2, "2 of 16 batch elements (one GPU's share at 8 GPUs)"),
                           ("sdpa_cfg5_whole", 16, "all 16 batch elements on one GPU")):
         qs, ks, vs = (torch.empty(Bd, S, H, D, dtype=torch.bfloat16, device=dev).normal_().transpose(1, 2)
                       for _ in range(3))
-        ms = _time_gpu(lambda: sdpa(qs, ks, vs), 10 if Bd == 2 else 4)
+        ms, ms_best = _time_gpu_burst(lambda: sdpa(qs, ks, vs), 10 if Bd == 2 else 6)
         flops = 4 * Bd * H * S * S * D
         out[key] = {"workload": f"MojoSdpa DiT 24 heads hd128 S=4096 non-causal bf16, {note}, transposed-BSHD views",
-                    "ms": ms, "tflops": flops / ms / 1e9,
+                    "ms": ms, "ms_best": ms_best, "tflops": flops / ms / 1e9, "tflops_best": flops / ms_best / 1e9,
                     "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"], "flops": flops}
         del qs, ks, vs
+    if args.sustain_s > 0:
+        ms, flops = out["prefill_cfg3"]["ms"], out["prefill_cfg3"]["flops"]
+        iters = max(10, int(2.0 * args.sustain_s * 1e3 / ms))
+        ms_s = _time_gpu(run_prefill, iters, warmup=1)
+        sus_peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+        out["prefill_cfg3"]["sustained"] = {"seconds": ms_s * iters * 1e-3, "launches": iters, "ms": ms_s,
+                                            "tflops": flops / ms_s / 1e9, "peak_sustained": sus_peak,
+                                            "frac_of_bf16_sustained_peak": flops / ms_s / 1e9 / sus_peak}
     return out
 
 

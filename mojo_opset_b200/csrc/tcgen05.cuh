@@ -318,16 +318,32 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   return d;
 }
 
-// 2^x for a pair on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
-// polynomial for 2^f (relative error 7.5e-5, far inside bf16/fp16 rounding of P), n added to the exponent field.
-// x is clamped at -125 so the exponent never underflows: masked scores give 2^-125 instead of 0.
-__device__ __forceinline__ float2 ex2_emulated2(float2 x) {
-  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
-  x.x = fmaxf(x.x, -125.f);
-  x.y = fmaxf(x.y, -125.f);
-  const float2 t = add2(x, make_float2(kMagic, kMagic));
-  const float2 r = add2(t, make_float2(-kMagic, -kMagic));
-  const float2 f = add2(x, make_float2(-r.x, -r.y));
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float d;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// exp2 of a pair on the FMA pipe (the MUFU runs 16 exponentials per clock and SM - as many cycles per attention tile
+// as the tensor cores need for its two products).  The caller passes y = sat((x + 125) / 256), computed with ONE
+// FFMA.SAT straight from the score: x is clamped to [-125, 131] for free and masked (-inf) scores become 2^-125.
+//   t = 256 y + K          K = 1.5 * 2^23 - 125: t = magic + n, n = round(x) sits in the low mantissa bits
+//   f = 256 y - (n + 125)  in [-0.5, 0.5]                      (exact: power-of-two scaling, integer n)
+//   2^x = p(f) * 2^n       p = degree-3 minimax polynomial (relative error 8e-5: far below the bf16 / fp16 rounding of
+//                          P), the exponent by adding n << 23 to the bit pattern (one LEA)
+// Cost per pair: 2 FFMA.SAT + 5 FFMA2 / FADD2 + 2 LEA against 1 FFMA2 + 2 MUFU.EX2 (16 MUFU-pipe cycles).
+__device__ __forceinline__ float2 ex2_fma_pipe2(float2 y) {
+  constexpr float kK = 12582912.f - 125.f;
+  const float2 t = fma2(y, make_float2(256.f, 256.f), make_float2(kK, kK));
+  const float2 mneg = sub2(make_float2(kK, kK), t);
+  const float2 f = fma2(y, make_float2(256.f, 256.f), mneg);
   float2 q = fma2(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
   q = fma2(q, f, make_float2(0.6932609677f, 0.6932609677f));
   q = fma2(q, f, make_float2(0.9999280572f, 0.9999280572f));
