@@ -65,6 +65,9 @@ constexpr float kRescaleThreshold = 8.f;      // log2 units
 #define MOJO_ATTN_EMU_PAIRS 2
 #endif
 constexpr int kEmuPairs = MOJO_ATTN_EMU_PAIRS;  // of every 8 pairs of exponentials, this many run on the FMA pipe
+#ifndef MOJO_ATTN_LAZY_REF
+#define MOJO_ATTN_LAZY_REF 1
+#endif
 #ifndef MOJO_ATTN_ROUND_DEFAULT
 #define MOJO_ATTN_ROUND_DEFAULT 0
 #endif
@@ -439,7 +442,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       const int tile_min_limit = CAUSAL ? min(kv_len - 1, off + first_row) : kv_len - 1;
       const int row_lo = win_lo(row), tile_max_lo = win_lo(first_row + kBM - 1);  // sliding-window lower bounds
       const float scale_log2 = p.scale_log2;
-      float m_ref = -INFINITY, l = 0.f;
+      float m_ref = -INFINITY, l = 0.f, pending = 0.f;
+      constexpr bool kLazyRef = MOJO_ATTN_LAZY_REF != 0 && std::is_same<T, __nv_bfloat16>::value;
+      // lazy reference = first tile's maximum + 60 (log2 units): exponentials sit around 2^-60, half way through the
+      // exponent range, so a tile may outgrow everything seen before it by 2^187 (130 nats) before anything overflows
+      // and keys more than 2^-66 below the reference row maximum flush to zero (their true weight is below 2^-66)
+      constexpr float kRefBias = kLazyRef ? 60.f : 0.f;
 
       // One softmax step as a generic lambda instantiated twice: MASKED = false is the hot body (no per-column compare
       // at all), MASKED = true carries the causal / tail / window compares of the few tiles an edge crosses.  Laid out
@@ -496,38 +504,60 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
               if (n0 + c < row_lo && n0 + c >= win_g) sr[c] = 0xff800000u;  // -inf
           }
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < kBN; c += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
-        }
-        const float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;  // scale > 0
-
-        if (j == 0) {
-          m_ref = mt;
-        } else {
-          const bool grow = mt > m_ref + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, grow)) {
-            // O_t is stable once PV_t(j-1) has completed
-            mbar_wait_bounded(&p_free[t], (uint32_t)(j - 1) & 1u);
-            tc_fence_after();
-            float alpha = 1.f;
-            if (grow) {
-              alpha = ex2_approx(m_ref - mt);
-              m_ref = mt;
-              l *= alpha;
-            }
+        // The softmax reference point m_ref only has to keep the exponentials in range - it need not be the row
+        // maximum: P is rounded relative to its own magnitude (bf16 has fp32's exponent range) and O, l are fp32, so
+        // any reference gives the same result.  bf16: the row maximum is computed for the FIRST tile only; later tiles
+        // reuse the reference and the tile's own sum (needed anyway) tells when the scores have grown (sum > 2^20):
+        // the reference moves by log2(sum) and O, l are rescaled at the start of the next step, after PV_t(j).  That
+        // removes the FMNMX pass (1 of ~6.75 issue cycles per score) from every other tile.  fp16 P has 5 exponent
+        // bits: it keeps the running maximum with lazy rescaling (threshold 2^8).  Limit of the lazy form: the scores
+        // of ONE 128-key tile may exceed everything the row has seen before by at most 2^187 (see kRefBias).
+        auto rescale_o = [&](float alpha) {
 #pragma unroll 1
-            for (int q4 = 0; q4 < 4; ++q4) {  // rare: kept as a real loop (code size)
-              uint32_t orow[32];
-              tmem_ld_x32(tO + q4 * 32, orow);
-              tmem_wait_ld();
+          for (int q4 = 0; q4 < 4; ++q4) {  // rare: kept as a real loop (code size)
+            uint32_t orow[32];
+            tmem_ld_x32(tO + q4 * 32, orow);
+            tmem_wait_ld();
 #pragma unroll
-              for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * alpha);
-              tmem_st_x32(tO + q4 * 32, orow);
+            for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * alpha);
+            tmem_st_x32(tO + q4 * 32, orow);
+          }
+        };
+        if (kLazyRef && j > 0 && __any_sync(0xffffffffu, pending != 0.f)) {
+          mbar_wait_bounded(&p_free[t], (uint32_t)(j - 1) & 1u);  // O_t is stable once PV_t(j-1) has completed
+          tc_fence_after();
+          const float alpha = ex2_approx(-pending);
+          m_ref += pending;
+          l *= alpha;
+          pending = 0.f;
+          rescale_o(alpha);
+        }
+        // rows that have not seen a key yet (m_ref = -inf: causal offset < 0, window skipping) still need a real reference
+        const bool exact_max = !kLazyRef || j == 0 || __any_sync(0xffffffffu, m_ref == -INFINITY);
+        if (exact_max) {
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < kBN; c += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
+            mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+          }
+          const float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;  // scale > 0
+          if (j == 0) {
+            m_ref = mt + kRefBias;
+          } else {
+            const bool grow = mt + kRefBias > m_ref + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, grow)) {
+              mbar_wait_bounded(&p_free[t], (uint32_t)(j - 1) & 1u);
+              tc_fence_after();
+              float alpha = 1.f;
+              if (grow) {
+                alpha = ex2_approx(m_ref - (mt + kRefBias));
+                m_ref = mt + kRefBias;
+                l *= alpha;
+              }
+              rescale_o(alpha);
             }
           }
         }
@@ -570,8 +600,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         }
         sum_a = add2(sum_a, sum_c);
         sum_b = add2(sum_b, sum_d);
-        const float sum0 = sum_a.x + sum_a.y, sum1 = sum_b.x + sum_b.y;
-        l += sum0 + sum1;
+        const float tile_sum = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+        l += tile_sum;
+        // the scores outgrew the reference (sum > 2^20 above the bias): move it by log2(sum) before the next tile
+        if (kLazyRef && tile_sum > 9.094947e-13f /* 2^(20 - 60) */)
+          pending = (float)(int)((__float_as_uint(tile_sum) >> 23) & 0xffu) - 127.f + kRefBias;
         if ((warp & 3) == MOJO_ATTN_TRACE_WARP) TRACE(t, j, 3);
         if (j > 0) {  // PV_t(j-1) has read P_t (long done: it was issued a whole softmax ago)
           mbar_wait_bounded(&p_free[t], (uint32_t)(j - 1) & 1u);
