@@ -84,6 +84,7 @@ struct Params {
   int max_blocks, block_size, log2_bs, box_rows, box_rows_v;
   int num_q_heads, num_kv_heads, group, interleave, dense;
   int batch, m_blocks;
+  unsigned tail_begin;  // single-CTA, non-causal: CTAs from this index on own ONE 128-row tile (two per grid unit)
   int pair_heads;  // PAIR: the two CTAs take two heads of one KV group (else two adjacent query blocks)
   // sliding window (MojoPagedPrefillSWA, causal only): key visible iff key + win_local >= position or key < win_global;
   // -1 = not set
@@ -134,7 +135,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   // 1-D grid in longest-processing-time order: CTAs are scheduled in linear order, so the query blocks with the most
   // keys (causal: the last ones) of EVERY (head, sequence) go first and the short ones fill the tail; heads vary
   // fastest so the q heads of one KV group run together and share K/V tiles in L2.
-  int hq, b, m_blk, m_blk_lead;
+  int hq, b, m_blk, m_blk_lead, half = -1;
   if (PAIR) {
     const unsigned cid = blockIdx.x >> 1;
     if (p.pair_heads) {  // two heads of one KV group, same query block
@@ -157,8 +158,17 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       m_blk = m_blk_lead + (int)rank;
     }
   } else {
-    hq = (int)(blockIdx.x % (unsigned)p.num_q_heads);
-    const int rest = (int)(blockIdx.x / (unsigned)p.num_q_heads);
+    // Tail of a non-causal grid: every CTA costs the same, so the last partial wave (r of the grid's units on r of the
+    // 148 SMs) would leave the other SMs idle for a whole CTA time.  The launcher turns those r units into 2r CTAs of
+    // ONE 128-row tile each (`half` = which tile): they finish in about half the time on twice as many SMs.
+    unsigned bid = blockIdx.x;
+    if (bid >= p.tail_begin) {
+      const unsigned e = bid - p.tail_begin;
+      half = (int)(e & 1u);
+      bid = p.tail_begin + (e >> 1);
+    }
+    hq = (int)(bid % (unsigned)p.num_q_heads);
+    const int rest = (int)(bid / (unsigned)p.num_q_heads);
     b = rest % p.batch;
     m_blk = m_blk_lead = p.m_blocks - 1 - rest / p.batch;
   }
@@ -174,10 +184,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
     q_len = p.cu_q[b + 1] - (int)q_start;
     kv_len = p.cu_kv ? p.cu_kv[b + 1] - p.cu_kv[b] : q_len;
   }
-  const int m0 = m_blk * 2 * kBM;
+  const int m0 = m_blk * 2 * kBM + (half > 0 ? kBM : 0);
   // everything that decides participation is computed from the LEADER's rows, so both CTAs of a pair agree (a peer
   // whose own rows are past the end still stages its operand halves and computes on rows nobody stores)
-  const int m0_lead = m_blk_lead * 2 * kBM;
+  const int m0_lead = m_blk_lead * 2 * kBM + (half > 0 ? kBM : 0);
   if (m0_lead >= q_len || kv_len <= 0) return;
   const int off = kv_len - q_len;  // query row t sees keys 0 .. off + t
   int n_t[2];
@@ -185,7 +195,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   for (int t = 0; t < 2; ++t) {
     const int first = m0_lead + t * kBM;
     int n = 0;
-    if (first < q_len) {
+    if (first < q_len && !(half >= 0 && t == 1)) {
       const int last = min(first + kBM, q_len) - 1;
       const int n_end = CAUSAL ? min(kv_len, off + last + 1) : kv_len;
       n = n_end > 0 ? (n_end + kBN - 1) / kBN : 0;
@@ -792,7 +802,15 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.win_local = a.causal ? a.win_local : -1; p.win_global = a.causal ? a.win_global : -1;
   const int64_t rows_per_step = (pair && !pair_heads) ? 4 * kBM : 2 * kBM;
   p.m_blocks = (int)((a.max_q_len + rows_per_step - 1) / rows_per_step);
-  const int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch * ((pair && !pair_heads) ? 2 : 1);
+  int64_t num_ctas = (int64_t)p.m_blocks * a.num_q_heads * a.batch * ((pair && !pair_heads) ? 2 : 1);
+  p.tail_begin = 0xffffffffu;
+  if (!pair && !a.causal && env_int("MOJO_B200_ATTN_SPLIT_TAIL", 1) != 0) {
+    const int64_t r = num_ctas % kNumSMs;
+    if (num_ctas > kNumSMs && r > 0 && r <= kNumSMs / 2) {
+      p.tail_begin = (unsigned)(num_ctas - r);
+      num_ctas += r;
+    }
+  }
   MOJO_REQUIRE(num_ctas <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "attention: grid too large");
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
