@@ -53,6 +53,14 @@ MOJO_B200_API const char* mojo_b200_last_error(void);
 /* 1 if the current device is compute capability 10.x, 0 otherwise, <0 / >0 on error. */
 MOJO_B200_API int mojo_b200_device_ok(void);
 
+/* Device error word.  The reference raises ValueError when a sequence with kv_len > 0 has no first block
+ * (mojo_opset/core/operators/attention.py:186-187 decode, :396-397 prefill) - a host read of the block table.  Here the
+ * caller registers one int32 of DEVICE memory per device (null = none); the attention kernels OR a bit into it when they
+ * meet such a row (and treat the unmapped keys as zeros); the caller reads and clears it when convenient. */
+#define MOJO_B200_ERR_DECODE_UNMAPPED_BLOCK 1
+#define MOJO_B200_ERR_PREFILL_UNMAPPED_BLOCK 2
+MOJO_B200_API int mojo_b200_set_error_word(int* device_word);
+
 /* ---------------------------------------------------------------------------------------------------
  * MojoStorePagedKVCache.forward                     mojo_opset/core/operators/kv_cache.py:110-171
  *
@@ -234,6 +242,19 @@ MOJO_B200_API int mojo_b200_sdpa(const void* query, const void* key, const void*
                    int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_s,
                    int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
                    float softmax_scale, int dtype, void* stream);
+
+/* The same with `attn_mask` (reference attention.py:466-501 passes it to F.scaled_dot_product_attention; reference test
+ * tests/accuracy/operators/test_attention.py:899-922: a [S, S] bool block-diffusion mask, 5 q / 1 kv heads): `mask` is
+ * bool bytes (1 = the key takes part) addressed [b, h, q, k] through byte strides (0 = broadcast over that dimension), keys
+ * contiguous.  A query row without any visible key reads as zeros (ATen returns NaN there). */
+MOJO_B200_API int mojo_b200_sdpa_masked(const void* query, const void* key, const void* value, void* out,
+                   int batch, int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
+                   int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                   int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s,
+                   int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_s,
+                   int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
+                   float softmax_scale, const void* mask, int64_t mask_stride_b, int64_t mask_stride_h,
+                   int64_t mask_stride_q, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * MojoGemmAllReduce.forward           mojo_opset/core/operators/compute_with_comm.py:57-117

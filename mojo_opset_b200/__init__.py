@@ -15,5 +15,6 @@ There is no CPU fallback anywhere: without an sm_100 GPU and the built ``libmojo
 from . import core
 from .core import *  # noqa: F401,F403
 from . import backends  # noqa: F401  (registers the B200* classes on an sm_100 platform)
+from ._lib import check_device_errors  # noqa: F401  (data errors the kernels flagged on the device -> ValueError)
 
 __version__ = "0.1.0"

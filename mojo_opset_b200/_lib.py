@@ -32,6 +32,7 @@ SIGNATURES = {
     "mojo_b200_abi_version": (I, []),
     "mojo_b200_last_error": (c_char_p, []),
     "mojo_b200_device_ok": (I, []),
+    "mojo_b200_set_error_word": (I, [P]),
     "mojo_b200_store_paged_kv_chunks": (I, [P, P, P, P, P, L, L, I, I, L, I] + [L] * 10 + [I, P]),
     "mojo_b200_store_paged_kv_table": (I, [P, P, P, P, P, L, I, P, P, I, L, I, I, L, I] + [L] * 10 + [I, P]),
     "mojo_b200_rms_norm": (I, [P, P, P, L, I, L, L, F, I, P]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "mojo_b200_paged_prefill_swa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10
                                     + [F, I, I, I, I, I, P]),
     "mojo_b200_sdpa": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, I, P]),
+    "mojo_b200_sdpa_masked": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, P, L, L, L, I, P]),
     "mojo_b200_norm_rope_store_kv": (I, [P, P, P, P, P, F, P, P, P, P, P, P, P, L, I, P, P, I, L, I, I, I, I, L, I]
                                      + [L] * 17 + [I, I, P]),
     "mojo_b200_gelu": (I, [P, P, L, L, L, L, I, P]),
@@ -124,6 +126,44 @@ def check(lib, rc: int, what: str) -> None:
     if rc == EINVAL:
         raise ValueError(msg)
     raise RuntimeError(f"{msg} (code {rc})")
+
+
+_error_words = {}
+
+ERR_DECODE_UNMAPPED_BLOCK, ERR_PREFILL_UNMAPPED_BLOCK = 1, 2
+
+
+def error_word(device) -> torch.Tensor:
+    """The int32 device word the kernels OR error bits into (one per device, registered with the library on first
+    use).  Allocated outside any graph capture by ``functional`` entry points that can raise data errors."""
+    device = torch.device(device)
+    index = torch.cuda.current_device() if device.index is None else device.index
+    word = _error_words.get(index)
+    if word is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None  # registered by the first eager call; kernels skip the check while there is no word
+        word = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", index))
+        with torch.cuda.device(index):
+            check(load(), load().mojo_b200_set_error_word(word.data_ptr()), "set_error_word")
+        _error_words[index] = word
+    return word
+
+
+def check_device_errors(device=None) -> None:
+    """Read (synchronises) and clear the device error word; raise what the reference raises on the host:
+    ``ValueError`` for a sequence with keys whose first block is unmapped (reference ``attention.py:186-187, 396-397``)."""
+    devices = list(_error_words) if device is None else [torch.device(device).index or 0]
+    for index in devices:
+        word = _error_words.get(index)
+        if word is None:
+            continue
+        bits = int(word.item())
+        if bits:
+            word.zero_()
+        if bits & ERR_DECODE_UNMAPPED_BLOCK:
+            raise ValueError("Paged decode requires a valid block table for rows with kv lens > 0.")
+        if bits & ERR_PREFILL_UNMAPPED_BLOCK:
+            raise ValueError("Paged prefill requires a valid block table for rows with kv lens > 0.")
 
 
 def ptr(t):

@@ -117,6 +117,4 @@ class B200Sdpa(MojoSdpa):
         value: torch.Tensor,
         attn_mask: Optional[torch.Tensor] = None,
     ):
-        if attn_mask is not None:
-            raise NotImplementedError("B200Sdpa does not take an attn_mask")
-        return F.sdpa(query, key, value, self.scale, self.enable_gqa)
+        return F.sdpa(query, key, value, self.scale, self.enable_gqa, attn_mask)

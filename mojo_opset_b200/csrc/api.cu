@@ -16,9 +16,29 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// Device error word: kernels cannot raise, and a host check of device data would synchronise (the reference's
+// `if block_tables[i, 0] < 0: raise ValueError` reads the table on the host, attention.py:186-187).  The caller
+// registers one int of device memory per device; kernels OR a MOJO_B200_ERR_* bit into it when they meet malformed
+// data and the caller reads it whenever it is convenient (mojo_opset_b200.check_device_errors()).
+static int* g_error_word[64] = {nullptr};
+
+int* error_word() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_error_word[dev];
+}
+
 }  // namespace mojo
 
 extern "C" {
+
+int mojo_b200_set_error_word(int* device_word) {
+  int dev = 0;
+  MOJO_CUDA_OK(cudaGetDevice(&dev));
+  MOJO_REQUIRE(dev >= 0 && dev < 64, MOJO_B200_EUNSUPPORTED, "set_error_word: device ordinal %d", dev);
+  mojo::g_error_word[dev] = device_word;
+  return 0;
+}
 
 int mojo_b200_abi_version(void) { return MOJO_B200_ABI_VERSION; }
 

@@ -47,6 +47,9 @@ struct AttnParams {
   // sliding-window attention (MojoPagedPrefillSWA / MojoPagedDecodeSWA): on top of the causal limit a key is visible
   // iff key + win_local >= position or key < win_global; -1 = that window is not set (both -1: plain causal)
   int win_local, win_global;
+  // MojoSdpa attn_mask (dense, non-causal): bool bytes, 1 = visible, strides in bytes per batch / head / row; null = none
+  const uint8_t* mask;
+  int64_t mask_sb, mask_sh, mask_sq;
 };
 
 template <typename T, int D, bool SPLIT_HALVES>
@@ -246,8 +249,15 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
       }
 
       // ---- rounding, scale, mask
-      const bool need_mask = n0 + kTile - 1 > warp_first_lim || valid < kTile ||
+      const bool need_mask = n0 + kTile - 1 > warp_first_lim || valid < kTile || p.mask != nullptr ||
                              (has_win && !(n0 >= warp_max_lo || n0 + kTile - 1 < win_g));
+      const uint8_t* mrow_lo = nullptr;
+      const uint8_t* mrow_hi = nullptr;
+      if (p.mask) {
+        const uint8_t* mb = p.mask + (int64_t)b * p.mask_sb + (int64_t)hq * p.mask_sh;
+        mrow_lo = mb + (int64_t)min(row_lo, q_len - 1) * p.mask_sq;
+        mrow_hi = mb + (int64_t)min(row_hi, q_len - 1) * p.mask_sq;
+      }
       float tile_lo = -INFINITY, tile_hi = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -258,6 +268,7 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
           if (need_mask) {
             const int key = n0 + j * 8 + 2 * c + (e & 1);
             if (key > (e < 2 ? lim_lo : lim_hi) || (key < (e < 2 ? lo_lo : lo_hi) && key >= win_g)) v = -INFINITY;
+            else if (p.mask && !(e < 2 ? mrow_lo : mrow_hi)[key]) v = -INFINITY;
           }
           s[j][e] = v;
           if (e < 2) tile_lo = fmaxf(tile_lo, v); else tile_hi = fmaxf(tile_hi, v);
@@ -405,7 +416,8 @@ static int launch_attn_mma(const KvDesc& kv, AttnParams& p, int head_dim, int dt
 // whose causal window is empty.  Usually none exist and every CTA exits at once; the host no longer memsets `out`.
 __global__ void prefill_zero_unseen_rows_kernel(void* out, const int32_t* cu_q, const int32_t* cu_kv, int batch,
                                                 int64_t total_q, int num_q_heads, int head_dim, int64_t o_st,
-                                                int64_t o_sh, int no_kv) {
+                                                int64_t o_sh, int no_kv, const int32_t* tables, int64_t table_stride,
+                                                int* err) {
   const int b = blockIdx.x;  // b == batch: the tail after the last sequence
   int64_t r0, r1;
   if (b == batch) {
@@ -415,6 +427,9 @@ __global__ void prefill_zero_unseen_rows_kernel(void* out, const int32_t* cu_q, 
     const int64_t q_start = cu_q[b];
     const int64_t q_len = cu_q[b + 1] - q_start;
     const int64_t kv_len = no_kv ? 0 : (cu_kv ? (int64_t)cu_kv[b + 1] - cu_kv[b] : q_len);
+    // the reference raises ValueError for a sequence with queries and keys but no first block (attention.py:396-397)
+    if (err && tables && blockIdx.y == 0 && threadIdx.x == 0 && q_len > 0 && kv_len > 0 && tables[b * table_stride] < 0)
+      atomicOr(err, 2);
     r0 = q_start;
     r1 = q_start + (kv_len <= 0 ? q_len : min(q_len, max((int64_t)0, q_len - kv_len)));
   }
@@ -467,7 +482,8 @@ static int paged_prefill_impl(
     // a global-only window of size 0 leaves no key visible to any row: every row reads as zero (both kernels)
     const int no_kv = max_blocks_per_seq == 0 || num_blocks == 0 || (win_local < 0 && win_global == 0);
     prefill_zero_unseen_rows_kernel<<<dim3((unsigned)batch + 1, 8), 256, 0, (cudaStream_t)stream>>>(
-        out, cu_q_lens, cu_total_seq_lens, batch, total_q_tokens, num_q_heads, head_dim, o_stride_t, o_stride_h, no_kv);
+        out, cu_q_lens, cu_total_seq_lens, batch, total_q_tokens, num_q_heads, head_dim, o_stride_t, o_stride_h, no_kv,
+        max_blocks_per_seq > 0 ? block_tables : nullptr, table_stride, error_word());
     const int rc = check_launch("prefill_zero_unseen_rows_kernel");
     if (rc != 0 || batch == 0 || no_kv) return rc;
   }
@@ -542,13 +558,16 @@ extern "C" int mojo_b200_paged_prefill_swa(
                             stream);
 }
 
-extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* value, void* out, int batch,
-                              int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
-                              int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s, int64_t k_stride_b,
-                              int64_t k_stride_h, int64_t k_stride_s, int64_t v_stride_b, int64_t v_stride_h,
-                              int64_t v_stride_s, int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
-                              float softmax_scale, int dtype, void* stream) {
+static int sdpa_impl(const void* query, const void* key, const void* value, void* out, int batch,
+                     int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
+                     int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s, int64_t k_stride_b,
+                     int64_t k_stride_h, int64_t k_stride_s, int64_t v_stride_b, int64_t v_stride_h,
+                     int64_t v_stride_s, int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
+                     float softmax_scale, const uint8_t* mask, int64_t mask_stride_b, int64_t mask_stride_h,
+                     int64_t mask_stride_q, int dtype, void* stream) {
   using namespace mojo;
+  MOJO_REQUIRE(mask == nullptr || (mask_stride_b >= 0 && mask_stride_h >= 0 && mask_stride_q >= 0), MOJO_B200_EINVAL,
+               "sdpa: negative mask stride");
   MOJO_REQUIRE(batch >= 0 && num_q_heads > 0 && num_kv_heads > 0 && q_len >= 0 && kv_len >= 0 && head_dim > 0,
                MOJO_B200_EINVAL, "sdpa: bad sizes");
   MOJO_REQUIRE(num_q_heads % num_kv_heads == 0, MOJO_B200_EINVAL, "sdpa: Hq %d not a multiple of Hkv %d", num_q_heads,
@@ -574,6 +593,7 @@ extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* va
     a.max_q_len = q_len; a.q_len_dense = q_len; a.kv_len_dense = kv_len; a.softmax_scale = softmax_scale;
     a.interleave = 0; a.causal = 0; a.dense = 1; a.round_scores = 0; a.dtype = dtype;
     a.win_local = a.win_global = -1;
+    a.mask = mask; a.mask_sb = mask_stride_b; a.mask_sh = mask_stride_h; a.mask_sq = mask_stride_q;
     const int rc = launch_attn_sm100(a, (cudaStream_t)stream);
     if (rc != kAttnNotEligible) return rc;
   }
@@ -581,6 +601,7 @@ extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* va
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = query; p.out = out;
+  p.mask = mask; p.mask_sb = mask_stride_b; p.mask_sh = mask_stride_h; p.mask_sq = mask_stride_q;
   p.box_rows = kTile;
   p.num_q_heads = num_q_heads; p.num_kv_heads = num_kv_heads; p.group = num_q_heads / num_kv_heads;
   p.q_len_dense = q_len; p.kv_len_dense = kv_len;
@@ -594,4 +615,29 @@ extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* va
             num_kv_heads};
   dim3 grid((unsigned)((q_len + kBM - 1) / kBM), (unsigned)num_q_heads, (unsigned)batch);
   return launch_attn_mma(kv, p, head_dim, dtype, grid, (cudaStream_t)stream);
+}
+
+extern "C" int mojo_b200_sdpa(const void* query, const void* key, const void* value, void* out, int batch,
+                              int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
+                              int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s, int64_t k_stride_b,
+                              int64_t k_stride_h, int64_t k_stride_s, int64_t v_stride_b, int64_t v_stride_h,
+                              int64_t v_stride_s, int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
+                              float softmax_scale, int dtype, void* stream) {
+  return sdpa_impl(query, key, value, out, batch, num_q_heads, num_kv_heads, q_len, kv_len, head_dim, q_stride_b,
+                   q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s, v_stride_b, v_stride_h, v_stride_s,
+                   o_stride_b, o_stride_h, o_stride_s, softmax_scale, nullptr, 0, 0, 0, dtype, stream);
+}
+
+extern "C" int mojo_b200_sdpa_masked(const void* query, const void* key, const void* value, void* out, int batch,
+                                     int num_q_heads, int num_kv_heads, int64_t q_len, int64_t kv_len, int head_dim,
+                                     int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s, int64_t k_stride_b,
+                                     int64_t k_stride_h, int64_t k_stride_s, int64_t v_stride_b, int64_t v_stride_h,
+                                     int64_t v_stride_s, int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s,
+                                     float softmax_scale, const void* mask, int64_t mask_stride_b,
+                                     int64_t mask_stride_h, int64_t mask_stride_q, int dtype, void* stream) {
+  MOJO_REQUIRE(mask != nullptr, MOJO_B200_EINVAL, "sdpa_masked: null mask");
+  return sdpa_impl(query, key, value, out, batch, num_q_heads, num_kv_heads, q_len, kv_len, head_dim, q_stride_b,
+                   q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s, v_stride_b, v_stride_h, v_stride_s,
+                   o_stride_b, o_stride_h, o_stride_s, softmax_scale, reinterpret_cast<const uint8_t*>(mask),
+                   mask_stride_b, mask_stride_h, mask_stride_q, dtype, stream);
 }

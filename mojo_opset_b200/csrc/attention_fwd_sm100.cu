@@ -91,6 +91,8 @@ struct Params {
   int win_local, win_global;
   int q_len_dense, kv_len_dense;
   float scale_log2;
+  const uint8_t* mask;  // MojoSdpa attn_mask (non-causal): bool bytes [.., q, k], 1 = visible; null = none
+  int64_t mask_sb, mask_sh, mask_sq;
   long long* trace;  // developer timeline (MOJO_ATTN_TRACE builds only, tools/attn_trace.py)
 };
 
@@ -508,6 +510,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
             for (int c = 0; c < kBN; ++c)
               if (n0 + c > limit) sr[c] = 0xff800000u;  // -inf
           }
+          if (!CAUSAL && p.mask != nullptr) {  // MojoSdpa attn_mask: this row's 128 bool bytes of the tile
+            const uint8_t* mrow = p.mask + (int64_t)b * p.mask_sb + (int64_t)hq * p.mask_sh +
+                                  (int64_t)min(row, q_len - 1) * p.mask_sq + n0;
+#pragma unroll
+            for (int c16 = 0; c16 < kBN / 16; ++c16) {
+              uint4 mb = make_uint4(0, 0, 0, 0);
+              if (n0 + c16 * 16 < kv_len) mb = *reinterpret_cast<const uint4*>(mrow + c16 * 16);  // (kv_len % 16 == 0)
+              const uint32_t w[4] = {mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if ((w[i >> 2] & (0xffu << (8 * (i & 3)))) == 0u) sr[c16 * 16 + i] = 0xff800000u;  // -inf
+            }
+          }
           if (HAS_WIN && has_win && !(n0 >= tile_max_lo || n0 + kBN - 1 < win_g)) {  // a window edge crosses this tile
 #pragma unroll
             for (int c = 0; c < kBN; ++c)
@@ -652,7 +667,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       for (int j = 0; j < n_tiles; ++j) {
         const int n0 = real_tile(j) * kBN;
         // a tile needs the compares iff a causal / tail edge or a window edge crosses it (uniform over the warpgroup)
-        const bool masked = n0 + kBN - 1 > tile_min_limit ||
+        const bool masked = n0 + kBN - 1 > tile_min_limit || (!CAUSAL && p.mask != nullptr) ||
                             (HAS_WIN && has_win && !(n0 >= tile_max_lo || n0 + kBN - 1 < win_g));
         if (masked) step(j, std::true_type{}); else step(j, std::false_type{});
       }
@@ -749,6 +764,8 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
     ok = ok && bs >= 8 && (bs & (bs - 1)) == 0;
     box_rows = bs < kBN ? (int)bs : kBN;
   }
+  if (a.mask) ok = ok && !a.causal && a.dense && a.kv_len_dense % 16 == 0 && a.mask_sq % 16 == 0 && a.mask_sb % 16 == 0 &&
+                a.mask_sh % 16 == 0 && aligned16(a.mask);  // 16-byte loads of a row's mask bytes
   // short query chunks leave most of a 256-row CTA idle: the 64-row general kernel is the better fit
   if (!forced && a.max_q_len < env_int("MOJO_B200_ATTN_TCGEN05_MIN_Q", 192)) ok = false;
   if (!ok) {
@@ -792,6 +809,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.num_kv_heads = a.num_kv_heads; p.group = a.num_q_heads / a.num_kv_heads; p.interleave = a.interleave;
   p.dense = a.dense; p.q_len_dense = (int)a.q_len_dense; p.kv_len_dense = (int)a.kv_len_dense;
   p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  p.mask = a.mask; p.mask_sb = a.mask_sb; p.mask_sh = a.mask_sh; p.mask_sq = a.mask_sq;
 #ifdef MOJO_ATTN_TRACE
   if (const char* tp = getenv("MOJO_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
 #endif

@@ -30,6 +30,10 @@ struct AttnSm100Args {
   float softmax_scale;
   int interleave, causal, dense, round_scores, dtype;
   int win_local, win_global;  // sliding window (causal only); -1 = not set
+  // MojoSdpa attn_mask (dense, non-causal only): bool bytes, 1 = the key takes part; element strides per batch / head /
+  // query row (0 = broadcast), keys contiguous; null = no mask
+  const uint8_t* mask;
+  int64_t mask_sb, mask_sh, mask_sq;
 };
 
 // 0 = launched; kAttnNotEligible = not covered (nothing was launched); anything else = error code.

@@ -18,6 +18,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // ---- error plumbing ------------------------------------------------------------------------------
 char* last_error_buffer();  // thread-local, defined in api.cu
 int fail(int code, const char* fmt, ...);
+int* error_word();  // the current device's registered error word (api.cu), or null
 
 #define MOJO_REQUIRE(cond, code, ...)                 \
   do {                                                \

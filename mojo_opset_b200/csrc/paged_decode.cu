@@ -55,6 +55,7 @@ struct DecodeParams {
   // MojoPagedDecodeSWA: the query token (position seq_len - 1) sees key k iff k + win_local >= position or
   // k < win_global; -1 = that window is not set (both -1: every key, MojoPagedDecodeGQA)
   int win_local, win_global;
+  int* err;  // device error word or null (include/mojo_b200.h)
 };
 
 __device__ __forceinline__ void split_tile_range(int seq_len, int num_splits, int split, int& tile_begin,
@@ -132,6 +133,10 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
   const int lane = threadIdx.x & 31;
   const int seq_len = p.seq_lens[b];
   const int rows_valid = min(16, p.group - ht * 16);  // query heads in this tile
+  // the reference raises ValueError for a row with keys but no first block (attention.py:186-187): flag it
+  if (p.err && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && seq_len > 0 && p.max_blocks > 0 &&
+      p.tables[(int64_t)b * p.table_stride] < 0)
+    atomicOr(p.err, 1);
 
   const DecodeWindow win = decode_window(seq_len, p.win_local, p.win_global);
   const bool swa = p.win_local >= 0 || p.win_global >= 0;
@@ -418,6 +423,9 @@ __global__ void __launch_bounds__(256) paged_decode_simt_kernel(const DecodePara
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq_len = p.seq_lens[b];
   const int rows_valid = min(GH, p.group - ht * GH);
+  if (p.err && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && seq_len > 0 && p.max_blocks > 0 &&
+      p.tables[(int64_t)b * p.table_stride] < 0)
+    atomicOr(p.err, 1);
 
   int tile_begin, tile_end;
   split_tile_range(seq_len, p.num_splits, split, tile_begin, tile_end);
@@ -663,6 +671,7 @@ static int paged_decode_impl(
   p.vc_b = vc_stride_b; p.vc_h = vc_stride_h; p.vc_t = vc_stride_t;
   p.scale = softmax_scale; p.interleave = gqa_interleave ? 1 : 0; p.num_splits = num_splits;
   p.win_local = win_local; p.win_global = win_global;
+  p.err = error_word();
 
   if (num_splits > 1) {
     const size_t need = mojo_b200_paged_decode_workspace_bytes(batch, num_q_heads, head_dim, num_splits);

@@ -358,6 +358,7 @@ def paged_decode_gqa(
     kc, vc = _inner_contiguous(key_cache), _inner_contiguous(value_cache)
     tables = block_tables if block_tables.stride(-1) == 1 or block_tables.shape[1] <= 1 else block_tables.contiguous()
     lens = total_seq_lens.contiguous()
+    _lib.error_word(dev)  # unmapped first blocks are flagged on the device (mojo_opset_b200.check_device_errors)
     out = torch.empty((batch, num_q_heads, head_dim), dtype=query.dtype, device=dev)
     if batch == 0:
         return out
@@ -431,6 +432,7 @@ def paged_prefill_gqa(
     tables = block_tables if block_tables.stride(-1) == 1 or block_tables.shape[1] <= 1 else block_tables.contiguous()
     cu_q = cu_q_lens.contiguous()
     cu_kv = None if cu_total_seq_lens is None else cu_total_seq_lens.contiguous()
+    _lib.error_word(dev)  # unmapped first blocks are flagged on the device (mojo_opset_b200.check_device_errors)
     # rows no query block covers (tokens past cu_q_lens[-1], sequences without keys) are zero-filled by the
     # library itself, as in the golden: no host-side memset of the whole output
     out = torch.empty((total_q, num_q_heads, head_dim), dtype=query.dtype, device=dev)
@@ -498,13 +500,33 @@ def paged_decode_swa(
                              max_total_seq_len, True, local_window_size, global_window_size)
 
 
+def _bool_mask_strides(attn_mask: torch.Tensor, batch: int, heads: int, q_len: int, kv_len: int):
+    """A bool ``attn_mask`` broadcastable to ``[B, Hq, Sq, Skv]`` as (uint8 view, byte strides b / h / q) with 0 for
+    broadcast dimensions; the key dimension must be dense (copied if it is not)."""
+    m = attn_mask
+    if m.dim() > 4:
+        raise ValueError(f"sdpa: attn_mask of rank {m.dim()} does not broadcast to [B, H, Sq, Skv]")
+    while m.dim() < 4:
+        m = m.unsqueeze(0)
+    want = (batch, heads, q_len, kv_len)
+    for have, full in zip(m.shape, want):
+        if have not in (1, full):
+            raise ValueError(f"sdpa: attn_mask shape {tuple(attn_mask.shape)} does not broadcast to {want}")
+    if m.shape[-1] != kv_len or (kv_len > 1 and m.stride(-1) != 1):
+        m = m.expand(m.shape[0], m.shape[1], m.shape[2], kv_len).contiguous()
+    strides = [0 if m.shape[i] == 1 else m.stride(i) for i in range(3)]
+    return m.view(torch.uint8), strides
+
+
 @_on_tensor_device
 def sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Optional[float] = None,
-         enable_gqa: bool = False) -> torch.Tensor:
+         enable_gqa: bool = False, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Non-causal dense attention.  ``[B,H,S,D]`` inputs may be transposed views of ``[B,S,H,D]`` memory (the
     DiT call site); the output is written as ``[B,S,H,D]`` memory and returned as the ``[B,H,S,D]`` view, which
-    is what the golden returns for such inputs and makes the caller's ``.transpose(1,2).contiguous()`` free."""
-    dev = _require_cuda(query, key, value)
+    is what the golden returns for such inputs and makes the caller's ``.transpose(1,2).contiguous()`` free.
+    ``attn_mask``: bool, broadcastable to ``[B, Hq, Sq, Skv]``, True = the key takes part (reference
+    ``attention.py:490-499``); additive float masks are not built."""
+    dev = _require_cuda(query, key, value, attn_mask)
     lib = _lib.load()
     if query.dim() != 4 or key.dim() != 4 or value.dim() != 4:
         raise NotImplementedError("sdpa: only [batch, heads, seq, head_dim] inputs are supported")
@@ -516,6 +538,8 @@ def sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Opt
         raise ValueError("sdpa: key/value shapes do not match query")
     if num_q_heads != num_kv_heads and not (enable_gqa and num_q_heads % num_kv_heads == 0):
         raise ValueError("sdpa: head counts differ; pass enable_gqa=True with Hq a multiple of Hkv")
+    if attn_mask is not None and attn_mask.dtype != torch.bool:
+        raise NotImplementedError("sdpa: only bool attn_mask is built (additive float masks are not)")
     if scale is None:
         scale = 1.0 / math.sqrt(head_dim)
     q, k, v = _inner_contiguous(query), _inner_contiguous(key), _inner_contiguous(value)
@@ -524,11 +548,16 @@ def sdpa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Opt
         return out
     if kv_len == 0:
         return out.zero_()
-    rc = lib.mojo_b200_sdpa(
+    common = (
         q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, num_q_heads, num_kv_heads, q_len, kv_len,
         head_dim, q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
-        v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
-        float(scale), _lib.dtype_id(query.dtype), _lib.stream_ptr(dev))
+        v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale))
+    if attn_mask is None:
+        rc = lib.mojo_b200_sdpa(*common, _lib.dtype_id(query.dtype), _lib.stream_ptr(dev))
+    else:
+        mask, (m_sb, m_sh, m_sq) = _bool_mask_strides(attn_mask, batch, num_q_heads, q_len, kv_len)
+        rc = lib.mojo_b200_sdpa_masked(*common, mask.data_ptr(), m_sb, m_sh, m_sq, _lib.dtype_id(query.dtype),
+                                       _lib.stream_ptr(dev))
     _lib.check(lib, rc, "sdpa")
     return out
 

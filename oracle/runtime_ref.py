@@ -1,7 +1,10 @@
 """TEST INFRASTRUCTURE - CPU restatement of the reference's paged-KV bookkeeping
 (``mojo_opset/runtime/runtime.py:112-158``: ``_allocate_blocks``, ``_reserve``, ``_build_positions``), used by
 ``tests/test_gpu_runtime.py`` to check that the device-side allocator hands out the same blocks in the same order.
-The product never imports it."""
+The product never imports it.
+
+Parity pin: ``tests/golden/runtime.pt`` (made by ``tests/golden/make_runtime_golden.py`` from the UNMODIFIED reference class) -
+``tests/test_oracle_golden.py::test_runtime_oracle_matches_reference_bookkeeping`` checks this file against it bit for bit."""
 
 import torch
 

@@ -273,3 +273,50 @@ def test_large_logit_jumps_between_tiles(F, impl, op, dtype):
         out = F.paged_prefill_gqa(q.to(DEV), kc.to(DEV), vc.to(DEV), cu.to(DEV), table.to(DEV), max_q_len=T)
     assert torch.isfinite(out.float()).all()
     torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)
+
+
+def _block_diffusion_mask(seq_length, block_size):
+    """The reference test's mask family (tests/accuracy/operators/test_attention.py:868-880): [2S, 2S] bool over a
+    (noisy | clean) sequence pair - same-block attention inside the noisy half, noisy -> earlier clean blocks, clean ->
+    block-causal clean."""
+    n = 2 * seq_length
+    idx = torch.arange(n)
+    blk = (idx % seq_length) // block_size
+    noisy = idx < seq_length
+    same_block = (noisy[:, None] & noisy[None, :]) & (blk[:, None] == blk[None, :])
+    cross = (noisy[:, None] & ~noisy[None, :]) & (blk[None, :] < blk[:, None])
+    lower_tri = (~noisy[:, None] & ~noisy[None, :]) & (blk[None, :] <= blk[:, None])
+    return same_block | cross | lower_tri
+
+
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma"])
+@pytest.mark.parametrize("shape", [(1, 5, 1, 2048, 32, 128), (2, 4, 2, 512, 64, 128), (1, 4, 2, 256, 32, 64)], ids=str)
+def test_sdpa_attn_mask_vs_oracle(F, impl, kernel, shape):
+    """MojoSdpa with a bool attn_mask (reference test_attention.py:899-922: 5 q / 1 kv heads, S = 2 x 2048, block 32),
+    through both kernels; [S,S], [B,1,S,S] and per-head masks; float masks are refused."""
+    from oracle import golden
+
+    B, Hq, Hkv, S, blk, D = shape
+    if kernel == "tcgen05" and D != 128:
+        pytest.skip("the tcgen05 kernel covers head_dim 128")
+    g = torch.Generator().manual_seed(9)
+    n = 2 * S
+    q = torch.randn(B, Hq, n, D, generator=g).to(torch.bfloat16)
+    k = torch.randn(B, Hkv, n, D, generator=g).to(torch.bfloat16)
+    v = torch.randn(B, Hkv, n, D, generator=g).to(torch.bfloat16)
+    mask = _block_diffusion_mask(S, blk)
+    impl(kernel)
+    ref = golden.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), mask.to(DEV), None, Hq != Hkv)   # the oracle on CUDA tensors
+    out = F.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), None, Hq != Hkv, mask.to(DEV))
+    torch.testing.assert_close(out.float(), ref.float(), **TOL)
+    # the same mask given per batch element / per head (strided, broadcast over heads)
+    mb = mask.expand(B, 1, n, n).to(DEV)
+    out_b = F.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), None, Hq != Hkv, mb)
+    assert torch.equal(out_b, out)
+    if B * Hq * n * n <= (1 << 27):
+        head_masks = torch.stack([mask if h % 2 == 0 else torch.ones_like(mask) for h in range(Hq)]).expand(B, Hq, n, n)
+        ref_h = golden.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), head_masks.to(DEV), None, Hq != Hkv)
+        out_h = F.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), None, Hq != Hkv, head_masks.contiguous().to(DEV))
+        torch.testing.assert_close(out_h.float(), ref_h.float(), **TOL)
+    with pytest.raises(NotImplementedError):
+        F.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), None, Hq != Hkv, torch.zeros(n, n, device=DEV))

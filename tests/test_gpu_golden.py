@@ -171,11 +171,7 @@ def test_paged_decode_swa_long(ops, local, glob, splits):
 @pytest.mark.parametrize("case", SDPA, ids=_ids(SDPA))
 def test_sdpa(ops, case):
     op = ops.MojoSdpa(scale=case["scale"], enable_gqa=case["enable_gqa"])
-    if case["attn_mask"] is not None:
-        with pytest.raises(NotImplementedError):
-            op(_cuda(case["query"]), _cuda(case["key"]), _cuda(case["value"]), _cuda(case["attn_mask"]))
-        return
-    out = op(_cuda(case["query"]), _cuda(case["key"]), _cuda(case["value"]))
+    out = op(_cuda(case["query"]), _cuda(case["key"]), _cuda(case["value"]), _cuda(case["attn_mask"]))
     assert out.shape == case["out"].shape
     torch.testing.assert_close(out.cpu().float(), case["out"].float(), atol=2e-2, rtol=2e-2)
 

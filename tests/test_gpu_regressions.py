@@ -77,3 +77,32 @@ def test_ops_run_on_the_tensors_device_not_the_current_one(ops):
     ref = golden.paged_decode_gqa(q, kc, vc, lens, table)
     torch.testing.assert_close(out.cpu().float(), ref.float(), atol=2e-2, rtol=2e-2)
     assert torch.cuda.current_device() == 0
+
+
+def test_unmapped_first_block_raises_value_error_like_the_reference(ops):
+    """Reference attention.py:186-187 / 396-397: a row with keys whose first block id is negative is a ValueError.  A host
+    check would synchronise; the kernels flag it in a device word that ``check_device_errors()`` turns into the error."""
+    import mojo_opset_b200 as m
+
+    B, Hq, Hkv, D, bs = 3, 8, 2, 128, 16
+    kc = torch.randn(12, Hkv, bs, D, device=DEV).to(torch.bfloat16)
+    vc = torch.randn(12, Hkv, bs, D, device=DEV).to(torch.bfloat16)
+    q = torch.randn(B, Hq, D, device=DEV).to(torch.bfloat16)
+    table = torch.tensor([[0, 1, 2], [-1, 4, 5], [6, 7, 8]], dtype=torch.int32, device=DEV)
+    lens = torch.tensor([40, 20, 0], dtype=torch.int32, device=DEV)
+    try:
+        m.check_device_errors()                  # clean slate (earlier tests may have fed unmapped tables on purpose)
+    except ValueError:
+        pass
+    ops.MojoPagedDecodeGQA()(q, kc, vc, lens, table)
+    with pytest.raises(ValueError, match="Paged decode requires a valid block table"):
+        m.check_device_errors()
+    m.check_device_errors()                      # the word was cleared
+    lens_ok = torch.tensor([40, 0, 0], dtype=torch.int32, device=DEV)   # the unmapped row has no keys: fine
+    ops.MojoPagedDecodeGQA()(q, kc, vc, lens_ok, table)
+    m.check_device_errors()
+    qp = torch.randn(30, Hq, D, device=DEV).to(torch.bfloat16)
+    cu = torch.tensor([0, 10, 30, 30], dtype=torch.int32, device=DEV)
+    ops.MojoPagedPrefillGQA()(qp, kc, vc, cu, table, max_q_len=20)
+    with pytest.raises(ValueError, match="Paged prefill requires a valid block table"):
+        m.check_device_errors()

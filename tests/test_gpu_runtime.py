@@ -44,6 +44,29 @@ def test_reserve_matches_reference_order():
         state.check()
 
 
+def test_device_allocator_replays_the_reference_trace():
+    """The device-side allocator against the states the UNMODIFIED reference's PagedAttentionRuntimeState went through
+    (tests/golden/runtime.pt, made by tests/golden/make_runtime_golden.py): same blocks, same order, same positions."""
+    from conftest import load_golden
+    from mojo_opset_b200.runtime import PagedAttentionRuntimeState
+
+    for case in load_golden("runtime.pt"):
+        state = PagedAttentionRuntimeState(1, 1, 8, case["batch"], case["max_position_embeddings"], DEV,
+                                           torch.bfloat16, block_size=case["block_size"])
+        for step in case["trace"]:
+            if step["kind"] == "prefill":
+                q = step["q_lens"]
+                _, pos, meta = state.prepare_prefill_inputs(torch.zeros(int(q.sum()), dtype=torch.int64), q)
+                assert torch.equal(meta.cu_q_lens.cpu(), step["cu_q_lens"])
+            else:
+                _, pos, meta = state.prepare_decode_inputs(torch.zeros(case["batch"], dtype=torch.int64, device=DEV))
+            assert torch.equal(pos.cpu(), step["positions"].to(torch.int64)), case["name"]
+            assert torch.equal(state.block_tables.cpu(), step["block_tables"]), case["name"]
+            assert torch.equal(state.total_seq_lens.cpu(), step["total_seq_lens"])
+            assert state.num_free_blocks == step["num_free_blocks"]
+        state.check()
+
+
 def test_reserve_out_of_memory_changes_nothing():
     from mojo_opset_b200.runtime import PagedAttentionRuntimeState
 

@@ -138,8 +138,6 @@ def test_contracts_raise_like_reference():
     with pytest.raises(AssertionError):  # cu_total_seq_lens must be cumulative [B+1]
         B200PagedPrefillGQA()(q, kc, kc, torch.tensor([0, 1, 2], dtype=torch.int32), tables, None,
                               torch.tensor([3, 4], dtype=torch.int32))
-    with pytest.raises(NotImplementedError):
-        B200Sdpa()(q[None], q[None], q[None], attn_mask=torch.ones(4, 4, dtype=torch.bool))
     with pytest.raises(AssertionError):  # mixing the plan with the legacy triple
         B200StorePagedKVCache()(q, q, kc, kc, tables, chunk_metadata=torch.zeros(1, 4, dtype=torch.int32))
     with pytest.raises(AssertionError):

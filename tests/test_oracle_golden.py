@@ -136,3 +136,32 @@ def test_c_oracle_store_kv_bit_exact(case):
     kc = store_kv_c.store_paged_kv(case["key_states"].contiguous(), case["key_cache"].clone(), plan)
     vc = store_kv_c.store_paged_kv(case["value_states"].contiguous(), case["value_cache"].clone(), plan)
     assert torch.equal(kc, case["key_cache_out"]) and torch.equal(vc, case["value_cache_out"])
+
+
+RUNTIME = load_golden("runtime.pt")
+
+
+@pytest.mark.parametrize("case", RUNTIME, ids=[c["name"] for c in RUNTIME])
+def test_runtime_oracle_matches_reference_bookkeeping(case):
+    """oracle/runtime_ref.py (the checker of the device-side block allocator) against the state the UNMODIFIED
+    reference's PagedAttentionRuntimeState went through (runtime/runtime.py:112-228): block tables, lengths, free
+    count, positions and the KV-store plan after every prefill / decode step - bit exact."""
+    from oracle import golden
+    from oracle.runtime_ref import ReserveOracle
+
+    o = ReserveOracle(case["batch"], case["max_position_embeddings"], case["block_size"])
+    for step in case["trace"]:
+        q = step["q_lens"]
+        ctx = o.reserve(q)
+        assert torch.equal(o.block_tables, step["block_tables"])
+        assert torch.equal(o.total_seq_lens, step["total_seq_lens"])
+        assert o.num_free_blocks == step["num_free_blocks"]
+        if step["kind"] == "prefill":
+            assert torch.equal(o.positions(ctx, q), step["positions"])
+            cu = torch.nn.functional.pad(q.cumsum(-1, dtype=torch.int32), (1, 0))
+            assert torch.equal(cu, step["cu_q_lens"])
+            plan = golden.build_chunk_plan(o.block_tables, cu, ctx, case["block_size"])
+        else:
+            assert torch.equal(ctx.to(torch.int64), step["positions"].to(torch.int64))
+            plan = golden.build_chunk_plan(o.block_tables, None, ctx, case["block_size"])
+        assert torch.equal(plan, step["chunk_metadata"])
