@@ -230,6 +230,20 @@ MOJO_B200_API int mojo_b200_paged_prefill_swa(
     int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * MojoSWA.forward (non-paged)                       mojo_opset/core/operators/attention.py:747-838
+ *
+ * query [Tq, Hq, D]; key / value PACKED [Tk, Hkv, D] (token, head strides): sequence b owns query rows
+ * cu_q_lens[b] .. cu_q_lens[b+1] and key rows cu_total_seq_lens[b] .. cu_total_seq_lens[b+1]; causal with offset
+ * kv_len - q_len and the window rule of the paged SWA ops (-1 = window not set).  is_causal = 0 is not built.
+ * ------------------------------------------------------------------------------------------------- */
+MOJO_B200_API int mojo_b200_swa(
+    const void* query, const void* key, const void* value, const int32_t* cu_q_lens, const int32_t* cu_total_seq_lens,
+    void* out, int64_t total_q_tokens, int64_t total_kv_tokens, int batch, int num_q_heads, int num_kv_heads, int head_dim,
+    int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h, int64_t o_stride_t, int64_t o_stride_h,
+    int64_t k_stride_t, int64_t k_stride_h, int64_t v_stride_t, int64_t v_stride_h, float softmax_scale,
+    int gqa_interleave, int is_causal, int local_window_size, int global_window_size, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * MojoSdpa.forward                                  mojo_opset/core/operators/attention.py:466-501
  *
  * query [B, Hq, Sq, D], key/value [B, Hkv, Skv, D] through (b, h, s) strides (D contiguous), no mask,

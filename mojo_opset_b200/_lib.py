@@ -50,6 +50,7 @@ SIGNATURES = {
                                     + [F, I, I, I, P]),
     "mojo_b200_paged_prefill_swa": (I, [P, P, P, P, P, P, P, L, I, I, I, I, L, I, I, L, L, L] + [L] * 10
                                     + [F, I, I, I, I, I, P]),
+    "mojo_b200_swa": (I, [P, P, P, P, P, P, L, L, I, I, I, I] + [L] * 10 + [F, I, I, I, I, I, P]),
     "mojo_b200_sdpa": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, I, P]),
     "mojo_b200_sdpa_masked": (I, [P, P, P, P, I, I, I, L, L, I] + [L] * 12 + [F, P, L, L, L, I, P]),
     "mojo_b200_norm_rope_store_kv": (I, [P, P, P, P, P, F, P, P, P, P, P, P, P, L, I, P, P, I, L, I, I, I, I, L, I]

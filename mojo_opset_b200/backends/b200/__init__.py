@@ -7,6 +7,7 @@ from .operators.attention import B200PagedDecodeGQA
 from .operators.attention import B200PagedDecodeSWA
 from .operators.attention import B200PagedPrefillGQA
 from .operators.attention import B200PagedPrefillSWA
+from .operators.attention import B200SWA
 from .operators.attention import B200Sdpa
 from .operators.compute_with_comm import B200GemmAllReduce
 from .operators.fused_attention_input import B200NormRoPEStoreKV
@@ -26,6 +27,7 @@ __all__ = [
     "B200PagedDecodeGQA",
     "B200PagedPrefillGQA",
     "B200PagedPrefillSWA",
+    "B200SWA",
     "B200PagedDecodeSWA",
     "B200Sdpa",
     "B200GemmAllReduce",

@@ -8,6 +8,7 @@ from mojo_opset_b200.core import MojoPagedDecodeSWA
 from mojo_opset_b200.core import MojoPagedPrefillGQA
 from mojo_opset_b200.core import MojoPagedPrefillSWA
 from mojo_opset_b200.core import MojoSdpa
+from mojo_opset_b200.core import MojoSWA
 from mojo_opset_b200.core.operators.attention import assert_paged_decode_contract
 from mojo_opset_b200.core.operators.attention import assert_paged_prefill_contract
 
@@ -105,6 +106,26 @@ class B200PagedDecodeSWA(MojoPagedDecodeSWA):
             raise NotImplementedError("B200PagedDecodeSWA supports is_causal=True only")
         return F.paged_decode_swa(query, key_cache, value_cache, total_seq_lens, block_table, softmax_scale,
                                   self.gqa_layout, max_total_seq_len, self.local_window_size, self.global_window_size)
+
+
+class B200SWA(MojoSWA):
+    supported_platforms_list = ["b200"]
+
+    def forward(
+        self,
+        query: torch.Tensor,
+        key: torch.Tensor,
+        value: torch.Tensor,
+        cu_q_lens: torch.Tensor,
+        cu_total_seq_lens: torch.Tensor,
+        softmax_scale: Optional[float] = None,
+    ):
+        assert cu_q_lens.dtype == torch.int32
+        assert cu_total_seq_lens.dtype == torch.int32
+        if not self.is_causal:  # the reference ignores the windows then: full attention inside each sequence
+            raise NotImplementedError("B200SWA supports is_causal=True only")
+        return F.swa(query, key, value, cu_q_lens, cu_total_seq_lens, softmax_scale, self.gqa_layout,
+                     self.local_window_size, self.global_window_size)
 
 
 class B200Sdpa(MojoSdpa):

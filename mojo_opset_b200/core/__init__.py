@@ -10,6 +10,7 @@ from .operators.attention import MojoPagedDecodeGQA
 from .operators.attention import MojoPagedDecodeSWA
 from .operators.attention import MojoPagedPrefillGQA
 from .operators.attention import MojoPagedPrefillSWA
+from .operators.attention import MojoSWA
 from .operators.attention import MojoSdpa
 from .operators.compute_with_comm import MojoGemmAllReduce
 from .operators.fused_attention_input import MojoNormRoPEStoreKV
@@ -32,6 +33,7 @@ __all__ = [
     "MojoPagedDecodeGQA",
     "MojoPagedPrefillGQA",
     "MojoPagedPrefillSWA",
+    "MojoSWA",
     "MojoPagedDecodeSWA",
     "MojoSdpa",
     "MojoGemmAllReduce",

@@ -167,6 +167,29 @@ class MojoPagedDecodeSWA(_PagedSWABase, MojoOperator):
         return MojoOperator.forward(self)
 
 
+class MojoSWA(_PagedSWABase, MojoOperator):
+    """Non-paged sliding-window attention over PACKED var-len tensors (reference ``attention.py:747-838``):
+    ``query[Tq,Hq,D]``, ``key/value[Tk,Hkv,D]``; sequence ``b`` owns query rows ``cu_q_lens[b]:cu_q_lens[b+1]`` and key
+    rows ``cu_total_seq_lens[b]:cu_total_seq_lens[b+1]``; causal with offset ``kv_len - q_len`` plus the window rule of
+    the paged SWA ops."""
+
+    def __init__(self, is_causal: bool = True, gqa_layout: str = "AABB", global_window_size: Optional[int] = None,
+                 local_window_size: Optional[int] = None):
+        super().__init__()
+        self._init_swa(is_causal, gqa_layout, global_window_size, local_window_size)
+
+    def forward(
+        self,
+        query: torch.Tensor,
+        key: torch.Tensor,
+        value: torch.Tensor,
+        cu_q_lens: torch.Tensor,
+        cu_total_seq_lens: torch.Tensor,
+        softmax_scale: Optional[float] = None,
+    ):
+        return MojoOperator.forward(self)
+
+
 class MojoSdpa(MojoOperator):
     """Dense non-causal SDPA ``[B,Hq,Sq,D] x [B,Hkv,Skv,D]`` (inputs may be strided views)."""
 

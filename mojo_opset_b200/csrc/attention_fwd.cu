@@ -44,6 +44,7 @@ struct AttnParams {
   int64_t q_st, q_sh, q_sb, o_st, o_sh, o_sb;
   float scale_log2;  // softmax_scale * log2(e)
   int interleave, causal, dense, stages, round_scores;
+  int packed;  // K/V are [total tokens, heads, D]: sequence b at rows cu_kv[b].. (non-paged MojoSWA)
   // sliding-window attention (MojoPagedPrefillSWA / MojoPagedDecodeSWA): on top of the causal limit a key is visible
   // iff key + win_local >= position or key < win_global; -1 = that window is not set (both -1: plain causal)
   int win_local, win_global;
@@ -73,7 +74,7 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int64_t q_start;
-  int q_len, kv_len;
+  int q_len, kv_len, kv_start = 0;
   if (p.dense) {
     q_start = 0;
     q_len = (int)p.q_len_dense;
@@ -82,6 +83,7 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
     q_start = p.cu_q[b];
     q_len = p.cu_q[b + 1] - (int)q_start;
     kv_len = p.cu_kv ? p.cu_kv[b + 1] - p.cu_kv[b] : q_len;
+    kv_start = p.cu_kv ? p.cu_kv[b] : (int)q_start;
   }
   const int m0 = q_tile * kBM;
   if (m0 >= q_len || kv_len <= 0) return;
@@ -121,7 +123,7 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
       tma_prefetch_desc(&k_map);
       tma_prefetch_desc(&v_map);
     }
-    const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
+    const int32_t* table = (p.dense || p.packed) ? nullptr : p.tables + (int64_t)b * p.table_stride;
     const uint32_t box_bytes = (uint32_t)box_rows * D * 2;
     for (int it = 0, use = 0; it < n_tiles; ++it) {
       if (!tile_live(it)) continue;
@@ -136,6 +138,9 @@ attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_cons
         if (p.dense) {
           blk = b;
           row_in_page = tok;
+        } else if (p.packed) {
+          blk = 0;
+          row_in_page = kv_start + tok;
         } else {
           const int page = tok >> p.log2_bs;
           row_in_page = tok & (p.block_size - 1);
@@ -457,7 +462,7 @@ static int paged_prefill_impl(
     int64_t table_stride, int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h,
     int64_t o_stride_t, int64_t o_stride_h, int64_t kc_stride_b, int64_t kc_stride_h, int64_t kc_stride_t,
     int64_t vc_stride_b, int64_t vc_stride_h, int64_t vc_stride_t, float softmax_scale, int gqa_interleave,
-    int is_causal, int win_local, int win_global, int dtype, void* stream) {
+    int is_causal, int win_local, int win_global, int dtype, void* stream, int packed = 0) {
   using namespace mojo;
   (void)max_kv_len;
   MOJO_REQUIRE(total_q_tokens >= 0 && batch >= 0 && num_q_heads > 0 && num_kv_heads > 0 && head_dim > 0 &&
@@ -466,14 +471,14 @@ static int paged_prefill_impl(
   MOJO_REQUIRE(num_q_heads % num_kv_heads == 0, MOJO_B200_EINVAL, "paged_prefill: Hq %d not a multiple of Hkv %d",
                num_q_heads, num_kv_heads);
   if (total_q_tokens == 0) return 0;
-  MOJO_REQUIRE(query && key_cache && value_cache && cu_q_lens && block_tables && out, MOJO_B200_EINVAL,
+  MOJO_REQUIRE(query && key_cache && value_cache && cu_q_lens && (block_tables || packed) && out, MOJO_B200_EINVAL,
                "paged_prefill: null tensor pointer");
   MOJO_REQUIRE(is_causal, MOJO_B200_EUNSUPPORTED, "paged_prefill: only causal attention is built");
   MOJO_REQUIRE(dtype == MOJO_B200_BF16 || dtype == MOJO_B200_F16, MOJO_B200_EUNSUPPORTED,
                "paged_prefill: bf16/fp16 only (tensor-core path)");
   MOJO_REQUIRE(head_dim == 64 || head_dim == 128, MOJO_B200_EUNSUPPORTED, "paged_prefill: head_dim %d not in {64,128}",
                head_dim);
-  MOJO_REQUIRE(block_size >= 8 && (block_size & (block_size - 1)) == 0, MOJO_B200_EUNSUPPORTED,
+  MOJO_REQUIRE(packed || (block_size >= 8 && (block_size & (block_size - 1)) == 0), MOJO_B200_EUNSUPPORTED,
                "paged_prefill: block_size %d must be a power of two >= 8", block_size);
   MOJO_REQUIRE(batch <= 65535 && num_q_heads <= 65535, MOJO_B200_EUNSUPPORTED, "paged_prefill: grid too large");
   MOJO_REQUIRE(head_dim % 2 == 0 && ((o_stride_t | o_stride_h) % 2) == 0 && ((uintptr_t)out & 3) == 0,
@@ -483,7 +488,7 @@ static int paged_prefill_impl(
     const int no_kv = max_blocks_per_seq == 0 || num_blocks == 0 || (win_local < 0 && win_global == 0);
     prefill_zero_unseen_rows_kernel<<<dim3((unsigned)batch + 1, 8), 256, 0, (cudaStream_t)stream>>>(
         out, cu_q_lens, cu_total_seq_lens, batch, total_q_tokens, num_q_heads, head_dim, o_stride_t, o_stride_h, no_kv,
-        max_blocks_per_seq > 0 ? block_tables : nullptr, table_stride, error_word());
+        max_blocks_per_seq > 0 && !packed ? block_tables : nullptr, table_stride, error_word());
     const int rc = check_launch("prefill_zero_unseen_rows_kernel");
     if (rc != 0 || batch == 0 || no_kv) return rc;
   }
@@ -502,6 +507,7 @@ static int paged_prefill_impl(
     a.max_blocks = max_blocks_per_seq; a.batch = batch; a.num_q_heads = num_q_heads; a.num_kv_heads = num_kv_heads;
     a.head_dim = head_dim; a.max_q_len = max_q_len; a.softmax_scale = softmax_scale;
     a.interleave = gqa_interleave ? 1 : 0; a.causal = 1; a.dense = 0; a.round_scores = 1; a.dtype = dtype;
+    a.packed = packed;
     const int rc = launch_attn_sm100(a, (cudaStream_t)stream);
     if (rc != kAttnNotEligible) return rc;
   }
@@ -510,8 +516,9 @@ static int paged_prefill_impl(
   memset(&p, 0, sizeof(p));
   p.q = query; p.out = out; p.cu_q = cu_q_lens; p.cu_kv = cu_total_seq_lens; p.tables = block_tables;
   p.table_stride = table_stride; p.max_blocks = max_blocks_per_seq; p.block_size = block_size;
-  while ((1 << p.log2_bs) < block_size) ++p.log2_bs;
-  p.box_rows = block_size < kTile ? block_size : kTile;
+  while (!packed && (1 << p.log2_bs) < block_size) ++p.log2_bs;
+  p.box_rows = (packed || block_size >= kTile) ? kTile : block_size;
+  p.packed = packed;
   p.num_q_heads = num_q_heads; p.num_kv_heads = num_kv_heads; p.group = num_q_heads / num_kv_heads;
   p.q_st = q_stride_t; p.q_sh = q_stride_h; p.q_sb = 0; p.o_st = o_stride_t; p.o_sh = o_stride_h; p.o_sb = 0;
   p.scale_log2 = softmax_scale * kLog2eF;
@@ -640,4 +647,25 @@ extern "C" int mojo_b200_sdpa_masked(const void* query, const void* key, const v
                    q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s, v_stride_b, v_stride_h, v_stride_s,
                    o_stride_b, o_stride_h, o_stride_s, softmax_scale, reinterpret_cast<const uint8_t*>(mask),
                    mask_stride_b, mask_stride_h, mask_stride_q, dtype, stream);
+}
+
+// MojoSWA (non-paged): the same kernels over PACKED key / value tensors [total_kv_tokens, Hkv, D] - sequence b owns rows
+// cu_total_seq_lens[b] .. cu_total_seq_lens[b+1] - instead of a paged cache.
+extern "C" int mojo_b200_swa(
+    const void* query, const void* key, const void* value, const int32_t* cu_q_lens, const int32_t* cu_total_seq_lens,
+    void* out, int64_t total_q_tokens, int64_t total_kv_tokens, int batch, int num_q_heads, int num_kv_heads, int head_dim,
+    int64_t max_q_len, int64_t max_kv_len, int64_t q_stride_t, int64_t q_stride_h, int64_t o_stride_t, int64_t o_stride_h,
+    int64_t k_stride_t, int64_t k_stride_h, int64_t v_stride_t, int64_t v_stride_h, float softmax_scale,
+    int gqa_interleave, int is_causal, int local_window_size, int global_window_size, int dtype, void* stream) {
+  using namespace mojo;
+  MOJO_REQUIRE(local_window_size >= -1 && global_window_size >= -1, MOJO_B200_EINVAL,
+               "swa: window sizes must be >= 0, or -1 for None");
+  MOJO_REQUIRE(cu_total_seq_lens != nullptr && total_kv_tokens > 0 && total_kv_tokens < (1LL << 31), MOJO_B200_EINVAL,
+               "swa: cu_total_seq_lens and a non-empty key tensor are required");
+  return paged_prefill_impl(query, key, value, cu_q_lens, cu_total_seq_lens, nullptr, out, total_q_tokens, batch,
+                            num_q_heads, num_kv_heads, head_dim, /*num_blocks=*/1, /*block_size=*/(int)total_kv_tokens,
+                            /*max_blocks_per_seq=*/1, 0, max_q_len, max_kv_len, q_stride_t, q_stride_h, o_stride_t,
+                            o_stride_h, total_kv_tokens * k_stride_t, k_stride_h, k_stride_t,
+                            total_kv_tokens * v_stride_t, v_stride_h, v_stride_t, softmax_scale, gqa_interleave, is_causal,
+                            local_window_size, global_window_size, dtype, stream, /*packed=*/1);
 }

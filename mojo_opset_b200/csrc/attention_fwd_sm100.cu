@@ -83,6 +83,7 @@ struct Params {
   int64_t o_sb, o_st, o_sh;
   int max_blocks, block_size, log2_bs, box_rows, box_rows_v;
   int num_q_heads, num_kv_heads, group, interleave, dense;
+  int packed;  // K/V are [total tokens, heads, D] tensors, sequence b at rows cu_kv[b].. (non-paged varlen)
   int batch, m_blocks;
   unsigned tail_begin;  // single-CTA, non-causal: CTAs from this index on own ONE 128-row tile (two per grid unit)
   int pair_heads;  // PAIR: the two CTAs take two heads of one KV group (else two adjacent query blocks)
@@ -176,7 +177,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
   }
 
   int64_t q_start;
-  int q_len, kv_len;
+  int q_len, kv_len, kv_start = 0;
   if (p.dense) {
     q_start = 0;
     q_len = p.q_len_dense;
@@ -185,6 +186,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
     q_start = p.cu_q[b];
     q_len = p.cu_q[b + 1] - (int)q_start;
     kv_len = p.cu_kv ? p.cu_kv[b + 1] - p.cu_kv[b] : q_len;
+    kv_start = p.cu_kv ? p.cu_kv[b] : (int)q_start;
   }
   const int m0 = m_blk * 2 * kBM + (half > 0 ? kBM : 0);
   // everything that decides participation is computed from the LEADER's rows, so both CTAs of a pair agree (a peer
@@ -279,7 +281,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           }
         }
       }
-      const int32_t* table = p.dense ? nullptr : p.tables + (int64_t)b * p.table_stride;
+      const int32_t* table = (p.dense || p.packed) ? nullptr : p.tables + (int64_t)b * p.table_stride;
       // ring items in the order the MMA warp first needs them: K(0) K(1) V(0) K(2) V(1) ... K(n-1) V(n-2) V(n-1)
       const uint32_t n_items = 2u * (uint32_t)n_max;
       {
@@ -299,7 +301,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           const int halves = (PAIR && is_v) ? 1 : 2;              // 64-column halves this CTA stages
           const uint32_t half_bytes = (uint32_t)rows * 128u;
           const uint32_t box_bytes = (uint32_t)box_rows * 128u;   // one half of one box
-          const int want = p.dense ? 1 : max(0, min(rows / box_rows, (kv_len - tok0 + box_rows - 1) / box_rows));
+          const int want = (p.dense || p.packed) ? 1 : max(0, min(rows / box_rows, (kv_len - tok0 + box_rows - 1) / box_rows));
           const uint32_t stage = ring_stage(c);
           uint8_t* dst = sKV + stage * kStageBytes;
 #ifdef MOJO_ATTN_DBG_NOTMA  // developer experiment: no K/V traffic after the first lap of the ring (results garbage)
@@ -325,6 +327,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
             if (p.dense) {
               blk = b;
               row = tok0;
+            } else if (p.packed) {  // rows past this sequence's end belong to the next one: masked / zeroed like a tail
+              blk = 0;
+              row = kv_start + tok0;
             } else {
               const int tok = tok0 + box * box_rows;
               const int page = tok >> p.log2_bs;
@@ -759,7 +764,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   ok = ok && (a.dense ? (a.q_sb % 8 == 0 && a.o_sb % 8 == 0) : true);
   ok = ok && aligned16(a.q) && aligned16(a.out) && aligned16(a.k) && aligned16(a.v);
   int box_rows = kBN;
-  if (!a.dense) {
+  if (!a.dense && !a.packed) {
     const int64_t bs = a.rows_per_block;
     ok = ok && bs >= 8 && (bs & (bs - 1)) == 0;
     box_rows = bs < kBN ? (int)bs : kBN;
@@ -786,8 +791,8 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   int box_rows_v = box_rows;
   if (pair) {  // a CTA stages 64 key rows of a K tile and all 128 key rows of one 64-column half of a V tile
     const int64_t bs = a.rows_per_block;
-    box_rows = a.dense ? kBN / 2 : (bs < kBN / 2 ? (int)bs : kBN / 2);
-    box_rows_v = a.dense ? kBN : (bs < kBN ? (int)bs : kBN);
+    box_rows = (a.dense || a.packed) ? kBN / 2 : (bs < kBN / 2 ? (int)bs : kBN / 2);
+    box_rows_v = (a.dense || a.packed) ? kBN : (bs < kBN ? (int)bs : kBN);
   }
 
   CUtensorMap q_map, k_map, v_map;
@@ -805,9 +810,9 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   p.cu_q = a.cu_q; p.cu_kv = a.cu_kv; p.tables = a.tables; p.table_stride = a.table_stride;
   p.o_sb = a.dense ? a.o_sb : 0; p.o_st = a.o_st; p.o_sh = a.o_sh;
   p.max_blocks = a.max_blocks; p.block_size = (int)a.rows_per_block; p.box_rows = box_rows; p.box_rows_v = box_rows_v;
-  while (!a.dense && (1 << p.log2_bs) < p.block_size) ++p.log2_bs;
+  while (!a.dense && !a.packed && (1 << p.log2_bs) < p.block_size) ++p.log2_bs;
   p.num_kv_heads = a.num_kv_heads; p.group = a.num_q_heads / a.num_kv_heads; p.interleave = a.interleave;
-  p.dense = a.dense; p.q_len_dense = (int)a.q_len_dense; p.kv_len_dense = (int)a.kv_len_dense;
+  p.dense = a.dense; p.packed = a.packed; p.q_len_dense = (int)a.q_len_dense; p.kv_len_dense = (int)a.kv_len_dense;
   p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
   p.mask = a.mask; p.mask_sb = a.mask_sb; p.mask_sh = a.mask_sh; p.mask_sq = a.mask_sq;
 #ifdef MOJO_ATTN_TRACE

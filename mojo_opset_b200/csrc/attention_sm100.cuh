@@ -34,6 +34,9 @@ struct AttnSm100Args {
   // query row (0 = broadcast), keys contiguous; null = no mask
   const uint8_t* mask;
   int64_t mask_sb, mask_sh, mask_sq;
+  // packed K/V (non-paged MojoSWA): key / value are [total_kv_tokens, heads, D]; sequence b owns rows
+  // cu_kv[b] .. cu_kv[b+1] (k_t = token stride, k_h = head stride, rows_per_block = total_kv_tokens, num_blocks = 1)
+  int packed;
 };
 
 // 0 = launched; kAttnNotEligible = not covered (nothing was launched); anything else = error code.

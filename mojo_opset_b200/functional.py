@@ -500,6 +500,49 @@ def paged_decode_swa(
                              max_total_seq_len, True, local_window_size, global_window_size)
 
 
+@_on_tensor_device
+def swa(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, cu_q_lens: torch.Tensor,
+        cu_total_seq_lens: torch.Tensor, softmax_scale: Optional[float] = None, gqa_layout: str = "AABB",
+        local_window_size: Optional[int] = None, global_window_size: Optional[int] = None,
+        max_q_len: Optional[int] = None, max_total_seq_len: Optional[int] = None) -> torch.Tensor:
+    """``MojoSWA`` (non-paged): causal sliding-window attention over packed ``query[Tq,Hq,D]`` / ``key, value[Tk,Hkv,D]``
+    with ``cu_q_lens`` / ``cu_total_seq_lens`` marking the sequences; the paged prefill kernels read the packed key /
+    value rows directly (no copy into pages).  Rows outside every sequence read as zeros."""
+    dev = _require_cuda(query, key, value, cu_q_lens, cu_total_seq_lens)
+    lib = _lib.load()
+    if query.dim() != 3 or key.dim() != 3 or key.shape != value.shape or key.shape[-1] != query.shape[-1]:
+        raise ValueError("swa: query [Tq, Hq, D], key / value [Tk, Hkv, D] expected")
+    if not (query.dtype == key.dtype == value.dtype):
+        raise NotImplementedError("swa: query, key and value must share one dtype")
+    total_q, num_q_heads, head_dim = query.shape
+    total_kv, num_kv_heads, _ = key.shape
+    if num_q_heads % num_kv_heads:
+        raise ValueError("swa: num_q_heads must be a multiple of num_kv_heads")
+    for name, w in (("local_window_size", local_window_size), ("global_window_size", global_window_size)):
+        if w is not None and int(w) < 0:
+            raise ValueError(f"swa: {name} must be >= 0 or None")
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(head_dim)
+    q, k, v = _inner_contiguous(query), _inner_contiguous(key), _inner_contiguous(value)
+    out = torch.empty((total_q, num_q_heads, head_dim), dtype=query.dtype, device=dev)
+    if total_q == 0:
+        return out
+    if total_kv == 0:
+        return out.zero_()
+    batch = cu_q_lens.shape[0] - 1
+    q_hint = total_q if max_q_len is None else min(int(max_q_len), total_q)
+    kv_hint = total_kv if max_total_seq_len is None else min(int(max_total_seq_len), total_kv)
+    rc = lib.mojo_b200_swa(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), cu_q_lens.contiguous().data_ptr(),
+        cu_total_seq_lens.contiguous().data_ptr(), out.data_ptr(), total_q, total_kv, batch, num_q_heads, num_kv_heads,
+        head_dim, q_hint, kv_hint, q.stride(0), q.stride(1), out.stride(0), out.stride(1), k.stride(0), k.stride(1),
+        v.stride(0), v.stride(1), float(softmax_scale), 1 if gqa_layout == "ABAB" else 0, 1,
+        -1 if local_window_size is None else int(local_window_size),
+        -1 if global_window_size is None else int(global_window_size), _lib.dtype_id(query.dtype), _lib.stream_ptr(dev))
+    _lib.check(lib, rc, "swa")
+    return out
+
+
 def _bool_mask_strides(attn_mask: torch.Tensor, batch: int, heads: int, q_len: int, kv_len: int):
     """A bool ``attn_mask`` broadcastable to ``[B, Hq, Sq, Skv]`` as (uint8 view, byte strides b / h / q) with 0 for
     broadcast dimensions; the key dimension must be dense (copied if it is not)."""

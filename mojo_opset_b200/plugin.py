@@ -29,6 +29,7 @@ OPS = (
     "PagedPrefillGQA",
     "PagedPrefillSWA",
     "PagedDecodeSWA",
+    "SWA",
     "Sdpa",
     "StorePagedKVCache",
     "ResidualAddRMSNorm",

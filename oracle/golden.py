@@ -194,6 +194,38 @@ def paged_decode_swa(query, key_cache, value_cache, total_seq_lens, block_table,
                              local_window_size, global_window_size)
 
 
+def swa(query, key, value, cu_q_lens, cu_total_seq_lens, softmax_scale=None, gqa_layout: str = "AABB",
+        is_causal: bool = True, local_window_size=None, global_window_size=None):
+    """Non-paged ``MojoSWA.forward`` (attention.py:776-834): the paged SWA arithmetic over packed ``key/value[Tk,Hkv,D]``
+    rows ``cu_total_seq_lens[b] : cu_total_seq_lens[b+1]``.  Rows outside every sequence are left as zeros here (the
+    reference leaves them uninitialised)."""
+    total_q, num_q_heads, head_dim = query.shape
+    num_kv_heads = key.shape[1]
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(head_dim)
+    head_map = _kv_head_of_q_head(num_q_heads, num_kv_heads, gqa_layout, query.device)
+    out = torch.zeros_like(query)
+    cu_q, cu_kv = cu_q_lens.tolist(), cu_total_seq_lens.tolist()
+    for b in range(len(cu_q) - 1):
+        lo, hi = cu_q[b], cu_q[b + 1]
+        q_len, kv_len = hi - lo, cu_kv[b + 1] - cu_kv[b]
+        if q_len == 0 or kv_len <= 0:
+            continue
+        k = key[cu_kv[b]:cu_kv[b + 1]][:, head_map]                                    # [kv, Hq, D]
+        v = value[cu_kv[b]:cu_kv[b + 1]][:, head_map]
+        q = query[lo:hi].permute(1, 0, 2)                                              # [Hq, q, D]
+        scores = torch.bmm(q, k.permute(1, 2, 0)).float() * softmax_scale              # [Hq, q, kv]
+        if is_causal:
+            vis = window_mask(q_len, kv_len, local_window_size, global_window_size).to(scores.device)
+            scores = torch.where(vis, scores, float("-inf"))
+        scores = scores - scores.max(dim=-1, keepdim=True).values
+        p = torch.exp(scores)
+        l = p.sum(dim=-1, keepdim=True)
+        o = torch.bmm(p.to(value.dtype), v.permute(1, 0, 2)).float() / l
+        out[lo:hi] = o.permute(1, 0, 2).to(out.dtype)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # a3  MojoSdpa.forward                      reference core/operators/attention.py:466-501
 # --------------------------------------------------------------------------------------------------

@@ -60,6 +60,14 @@ class TorchPagedDecodeSWA(core.MojoPagedDecodeSWA):
                                        self.gqa_layout, self.local_window_size, self.global_window_size)
 
 
+class TorchSWA(core.MojoSWA):
+    supported_platforms_list = ["b200", "meta_device"]
+
+    def forward(self, query, key, value, cu_q_lens, cu_total_seq_lens, softmax_scale=None):
+        return golden.swa(query, key, value, cu_q_lens, cu_total_seq_lens, softmax_scale, self.gqa_layout,
+                          self.is_causal, self.local_window_size, self.global_window_size)
+
+
 class TorchSdpa(core.MojoSdpa):
     supported_platforms_list = ["b200", "meta_device"]
 

@@ -254,3 +254,43 @@ def test_activation(ops, case):
     if sixteen_bit:  # same rounding points: only a last-place flip of the fp32 exp can show through
         assert (out.cpu() != case["out"]).float().mean().item() < 2e-3
         assert (s.cpu() != case["silu_out"]).float().mean().item() < 2e-3
+
+
+SWA_NONPAGED = load_golden("swa.pt")
+
+
+@pytest.mark.parametrize("case", SWA_NONPAGED, ids=_ids(SWA_NONPAGED))
+def test_nonpaged_swa(ops, case):
+    """MojoSWA (non-paged, packed var-len key / value) against the reference's outputs, through the op class -> C ABI."""
+    op = ops.MojoSWA(is_causal=True, gqa_layout=case["gqa_layout"], global_window_size=case["global_window_size"],
+                     local_window_size=case["local_window_size"])
+    assert type(op).__name__ == "B200SWA"
+    out = op(_cuda(case["query"]), _cuda(case["key"]), _cuda(case["value"]), _cuda(case["cu_q_lens"]),
+             _cuda(case["cu_total_seq_lens"]))
+    assert out.shape == case["out"].shape
+    torch.testing.assert_close(out.cpu().float(), case["out"].float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma"])
+def test_nonpaged_swa_long_ragged_vs_oracle(ops, kernel):
+    """Long ragged batch through both kernels (tile skipping, CTA pairs, keys of the NEXT sequence behind every tail)."""
+    from oracle import golden
+
+    os.environ["MOJO_B200_ATTN_IMPL"] = kernel
+    try:
+        g = torch.Generator().manual_seed(12)
+        q_lens, prefix = [900, 257, 1, 1500], [0, 700, 333, 100]
+        kv_lens = [a + b for a, b in zip(q_lens, prefix)]
+        Hq, Hkv, D = 8, 2, 128
+        q = torch.randn(sum(q_lens), Hq, D, generator=g).to(torch.bfloat16)
+        k = torch.randn(sum(kv_lens), Hkv, D, generator=g).to(torch.bfloat16)
+        v = torch.randn(sum(kv_lens), Hkv, D, generator=g).to(torch.bfloat16)
+        cu_q = torch.tensor([0] + torch.tensor(q_lens).cumsum(0).tolist(), dtype=torch.int32)
+        cu_kv = torch.tensor([0] + torch.tensor(kv_lens).cumsum(0).tolist(), dtype=torch.int32)
+        for local, glob in ((200, 40), (None, None), (1000, None)):
+            op = ops.MojoSWA(global_window_size=glob, local_window_size=local)
+            out = op(_cuda(q), _cuda(k), _cuda(v), _cuda(cu_q), _cuda(cu_kv))
+            ref = golden.swa(q, k, v, cu_q, cu_kv, None, "AABB", True, local, glob)
+            torch.testing.assert_close(out.cpu().float(), ref.float(), atol=2e-2, rtol=2e-2)
+    finally:
+        os.environ.pop("MOJO_B200_ATTN_IMPL", None)

@@ -100,10 +100,19 @@ ours, ref = pair("PagedDecodeSWA", is_causal=True, gqa_layout="AABB", global_win
 ours.forward_diff_with(ref, qd, kc, vc, lens, table, softmax_scale=None, atol=2e-2, rtol=2e-2)
 done.append("PagedDecodeSWA")
 
+# ---- MojoSWA (non-paged, packed var-len key / value)
+kpk, vpk = (torch.randn(sum(kv), 2, 128, device=DEV).to(bf) for _ in range(2))
+ours, ref = pair("SWA", is_causal=True, gqa_layout="AABB", global_window_size=16, local_window_size=100)
+ours.forward_diff_with(ref, q, kpk, vpk, cu_q, cu_kv, None, atol=2e-2, rtol=2e-2)
+done.append("SWA")
+
 # ---- MojoSdpa: DiT-shaped transposed views
 qs, ks, vs = (torch.randn(2, 640, 6, 128, device=DEV).to(bf).transpose(1, 2) for _ in range(3))
 ours, ref = pair("Sdpa")
 ours.forward_diff_with(ref, qs, ks, vs, atol=1e-2, rtol=1e-2)
+amask = torch.rand(640, 640, device=DEV) > 0.3
+amask[:, 0] = True
+ours.forward_diff_with(ref, qs, ks, vs, amask, atol=1e-2, rtol=1e-2)      # bool attn_mask
 done.append("Sdpa")
 
 # ---- MojoStorePagedKVCache: both signatures, bit exact

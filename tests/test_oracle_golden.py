@@ -165,3 +165,16 @@ def test_runtime_oracle_matches_reference_bookkeeping(case):
             assert torch.equal(ctx.to(torch.int64), step["positions"].to(torch.int64))
             plan = golden.build_chunk_plan(o.block_tables, None, ctx, case["block_size"])
         assert torch.equal(plan, step["chunk_metadata"])
+
+
+SWA_NONPAGED = load_golden("swa.pt")
+
+
+@pytest.mark.parametrize("case", SWA_NONPAGED, ids=[c["name"] for c in SWA_NONPAGED])
+def test_nonpaged_swa_oracle_matches_reference(case):
+    """oracle.golden.swa against the UNMODIFIED reference's MojoSWA outputs (tests/golden/make_swa_golden.py): bit exact."""
+    from oracle import golden
+
+    out = golden.swa(case["query"], case["key"], case["value"], case["cu_q_lens"], case["cu_total_seq_lens"], None,
+                     case["gqa_layout"], True, case["local_window_size"], case["global_window_size"])
+    assert torch.equal(out, case["out"])
