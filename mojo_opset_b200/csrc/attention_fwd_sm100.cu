@@ -110,15 +110,18 @@ struct Params {
 #define TRACE(role, j, ev) do {} while (0)
 #endif
 
-template <typename T, bool CAUSAL, bool ROUND_S, int EMU, bool PAIR, bool HAS_WIN>
+template <typename T, bool CAUSAL, bool ROUND_S, int EMU, bool PAIR, bool HAS_WIN, int D = 128>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map,
                       const __grid_constant__ CUtensorMap v_map, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  static_assert(D == 128 || (D == 64 && !PAIR), "head_dim 64 runs in single-CTA mode");
+  constexpr int kHalves = D / 64;                       // 64-column (128-byte) halves of a row
+  constexpr int kTileBytesD = kHalves * kHalfBytes;     // one Q / K / V tile of this head_dim
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + 2 * kTileBytes;
-  constexpr int kStages = PAIR ? 8 : 4;
+  constexpr int kStages = PAIR ? 8 : 4 * (2 / kHalves);  // head_dim 64: the same ring holds 8 tiles
   constexpr int kStageBytes = kRingBytes / kStages;
   auto ring_stage = [](uint32_t c) { return c % (uint32_t)kStages; };
   auto ring_parity = [](uint32_t c) { return (c / (uint32_t)kStages) & 1u; };
@@ -275,9 +278,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         for (int t = 0; t < 2; ++t) {
           if (n_t[t] > 0) {
             const int row0 = (int)q_start + m0 + t * kBM;
-            mbar_expect_tx(&q_full[t], kTileBytes);
-            tma_load_5d(sQ + t * kTileBytes, &q_map, &q_full[t], 0, row0, 0, hq, p.dense ? b : 0);
-            tma_load_5d(sQ + t * kTileBytes + kHalfBytes, &q_map, &q_full[t], 0, row0, 1, hq, p.dense ? b : 0);
+            mbar_expect_tx(&q_full[t], kTileBytesD);
+#pragma unroll
+            for (int h = 0; h < kHalves; ++h)
+              tma_load_5d(sQ + t * kTileBytesD + h * kHalfBytes, &q_map, &q_full[t], 0, row0, h, hq, p.dense ? b : 0);
           }
         }
       }
@@ -298,7 +302,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           const int box_rows = is_v ? p.box_rows_v : p.box_rows;
           const int rows = (PAIR && !is_v) ? kBN / 2 : kBN;       // key rows this CTA stages
           const int tok0 = real_tile(j) * kBN + ((PAIR && !is_v) ? (int)rank * (kBN / 2) : 0);
-          const int halves = (PAIR && is_v) ? 1 : 2;              // 64-column halves this CTA stages
+          const int halves = (PAIR && is_v) ? 1 : kHalves;        // 64-column halves this CTA stages
           const uint32_t half_bytes = (uint32_t)rows * 128u;
           const uint32_t box_bytes = (uint32_t)box_rows * 128u;   // one half of one box
           const int want = (p.dense || p.packed) ? 1 : max(0, min(rows / box_rows, (kv_len - tok0 + box_rows - 1) / box_rows));
@@ -322,7 +326,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           const CUtensorMap* map = is_v ? &v_map : &k_map;
           for (int idx = lane; idx < halves * want; idx += 32) {
             const int box = halves == 2 ? idx >> 1 : idx;
-            const int half = halves == 2 ? (idx & 1) : (int)rank;
+            const int half = halves == 2 ? (idx & 1) : (PAIR ? (int)rank : 0);
             int blk, row;
             if (p.dense) {
               blk = b;
@@ -369,7 +373,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
       constexpr int kM = PAIR ? 2 * kBM : kBM;  // PAIR: rows of both CTAs in one instruction
       constexpr uint32_t idesc_qk = umma_idesc_f16(kFmt, kM, kBN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(kFmt, kM, kD, 0, 1);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kFmt, kM, D, 0, 1);
       // K-major K operand: [64-column half][rows][128 B]; PAIR stages 64 of the 128 key rows per CTA
       constexpr uint32_t kKHalfStride = PAIR ? kHalfBytes / 2 : kHalfBytes;
       const uint32_t sQ_a = smem_u32(sQ), sKV_a = smem_u32(sKV);
@@ -394,9 +398,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           if (last_t >= 0) mbar_wait_bounded(&s_free[last_t], (uint32_t)last_j & 1u);
           TRACE(2, j, 4 + t);  // developer timeline: the wait for the S buffer returned
           tc_fence_after();
-          const uint64_t qd = umma_desc_sw128(sQ_a + t * kTileBytes, 16, 1024);
+          const uint64_t qd = umma_desc_sw128(sQ_a + t * kTileBytesD, 16, 1024);
           const uint64_t kd = umma_desc_sw128(sKV_a + k_stage * kStageBytes, 16, 1024);
           if (PAIR) umma_ss_x8_pair(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
+          else if (D == 64) umma_ss_x4(tmem, qd, kd, idesc_qk, 0);
           else umma_ss_x8(tmem, qd, kd, kHalfBytes >> 4, kKHalfStride >> 4, idesc_qk, 0);
           commit(&s_full[t]);
           TRACE(2, j, 2 * t);
@@ -424,8 +429,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           TRACE(2, j, 6 + t);      // developer timeline: the wait for P_t returned
           tc_fence_after();
           const uint64_t vd = umma_desc_sw128(sKV_a + v_stage * kStageBytes, kHalfBytes, 1024);
-          if (PAIR) umma_ts_x8_pair(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, j > 0);
-          else umma_ts_x8(tmem + 2 * kBN + t * kD, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, j > 0);
+          if (PAIR) umma_ts_x8_pair(tmem + 2 * kBN + t * D, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, j > 0);
+          else umma_ts_x8(tmem + 2 * kBN + t * D, tmem + kBN + t * (kBN / 2), vd, 2048 >> 4, idesc_pv, j > 0);
           commit(&p_free[t]);
           if (j == n_t[t] - 1) commit(&o_full[t]);
           TRACE(2, j, 1 + 2 * t);
@@ -450,7 +455,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t tS = tmem + lane_base;                                       // shared S buffer
       const uint32_t tP = tmem + lane_base + (uint32_t)(kBN + t * (kBN / 2));     // P_t (input dtype, 64 columns)
-      const uint32_t tO = tmem + lane_base + (uint32_t)(2 * kBN + t * kD);
+      const uint32_t tO = tmem + lane_base + (uint32_t)(2 * kBN + t * D);
       const uint32_t s_free_addr = PAIR ? mapa_u32(smem_u32(&s_free[t]), 0) : 0u;
       const uint32_t p_full_addr = PAIR ? mapa_u32(smem_u32(&p_full[t]), 0) : 0u;
       const int first_row = m0 + t * kBM;
@@ -544,7 +549,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
         // of ONE 128-key tile may exceed everything the row has seen before by at most 2^187 (see kRefBias).
         auto rescale_o = [&](float alpha) {
 #pragma unroll 1
-          for (int q4 = 0; q4 < 4; ++q4) {  // rare: kept as a real loop (code size)
+          for (int q4 = 0; q4 < D / 32; ++q4) {  // rare: kept as a real loop (code size)
             uint32_t orow[32];
             tmem_ld_x32(tO + q4 * 32, orow);
             tmem_wait_ld();
@@ -653,9 +658,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
           mbar_wait_bounded(&kv_full[ring_stage(cv)], ring_parity(cv));
           uint8_t* sv = sKV + ring_stage(cv) * kStageBytes;
           const int tid = threadIdx.x & 127;
-          constexpr int kChunks = PAIR ? 8 : 16;  // 16-byte chunks per key row staged by this CTA (one / two halves)
+          constexpr int kChunks = PAIR ? 8 : 8 * kHalves;  // 16-byte chunks per key row staged by this CTA
           for (int idx = tid; idx < (kBN - valid) * kChunks; idx += 128) {
-            const int r = valid + idx / kChunks, h = PAIR ? 0 : (idx >> 3) & 1, ch = idx & 7;
+            const int r = valid + idx / kChunks, h = kChunks == 16 ? (idx >> 3) & 1 : 0, ch = idx & 7;
             *reinterpret_cast<uint4*>(sv + h * kHalfBytes + r * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
           }
           fence_async_smem();
@@ -686,7 +691,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_co
       T* dst = reinterpret_cast<T*>(p.out) + (int64_t)b * p.o_sb + (q_start + row) * p.o_st + (int64_t)hq * p.o_sh;
       const bool row_ok = row < q_len;
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
+      for (int q4 = 0; q4 < D / 32; ++q4) {
         uint32_t orow[32];
         tmem_ld_x32(tO + q4 * 32, orow);
         tmem_wait_ld();
@@ -758,7 +763,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   const char* impl = getenv("MOJO_B200_ATTN_IMPL");  // "mma" forces the general path, "tcgen05" forbids it
   const bool forced = impl && !strcmp(impl, "tcgen05");
   if (impl && !strcmp(impl, "mma")) return kAttnNotEligible;
-  bool ok = a.head_dim == kD && (a.dtype == MOJO_B200_BF16 || a.dtype == MOJO_B200_F16) && a.softmax_scale > 0.f;
+  bool ok = (a.head_dim == 128 || a.head_dim == 64) && (a.dtype == MOJO_B200_BF16 || a.dtype == MOJO_B200_F16) && a.softmax_scale > 0.f;
   const int64_t strides[] = {a.k_b, a.k_h, a.k_t, a.v_b, a.v_h, a.v_t, a.q_st, a.q_sh, a.o_st, a.o_sh};
   for (int64_t st : strides) ok = ok && st > 0 && st % 8 == 0;
   ok = ok && (a.dense ? (a.q_sb % 8 == 0 && a.o_sb % 8 == 0) : true);
@@ -787,7 +792,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   // blocks (no GQA sharing) only pay off once the grid is several waves deep (DiT batch >= 4 of 24 x 4096 x 128)
   const int64_t ctas_single = ((a.max_q_len + 2 * kBM - 1) / (2 * kBM)) * a.num_q_heads * a.batch;
   const int pair_default = pair_heads ? 1 : (ctas_single >= 8 * 148 ? 1 : 0);
-  const bool pair = pair_ok && env_int("MOJO_B200_ATTN_PAIR", pair_default) != 0 && clusters_fit();
+  const bool pair = a.head_dim == 128 && pair_ok && env_int("MOJO_B200_ATTN_PAIR", pair_default) != 0 && clusters_fit();
   int box_rows_v = box_rows;
   if (pair) {  // a CTA stages 64 key rows of a K tile and all 128 key rows of one 64-column half of a V tile
     const int64_t bs = a.rows_per_block;
@@ -797,11 +802,11 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
 
   CUtensorMap q_map, k_map, v_map;
   const int64_t q_sb = a.dense ? a.q_sb : a.q_rows * a.q_st;  // paged: a single "batch" (any valid stride)
-  int rc = build_tile_map(a.q, a.dtype, a.q_rows, a.num_q_heads, a.dense ? a.batch : 1, q_sb, a.q_sh, a.q_st, kBM, &q_map);
+  int rc = build_tile_map(a.q, a.dtype, a.q_rows, a.num_q_heads, a.dense ? a.batch : 1, q_sb, a.q_sh, a.q_st, kBM, &q_map, a.head_dim / 64);
   if (rc != 0) return forced ? rc : kAttnNotEligible;
-  rc = build_tile_map(a.k, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.k_b, a.k_h, a.k_t, box_rows, &k_map);
+  rc = build_tile_map(a.k, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.k_b, a.k_h, a.k_t, box_rows, &k_map, a.head_dim / 64);
   if (rc != 0) return forced ? rc : kAttnNotEligible;
-  rc = build_tile_map(a.v, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.v_b, a.v_h, a.v_t, box_rows_v, &v_map);
+  rc = build_tile_map(a.v, a.dtype, a.rows_per_block, a.num_kv_heads, a.num_blocks, a.v_b, a.v_h, a.v_t, box_rows_v, &v_map, a.head_dim / 64);
   if (rc != 0) return forced ? rc : kAttnNotEligible;
 
   Params p;
@@ -846,15 +851,17 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pair ? 1 : 0;
-#define LAUNCH_SM100_P(TT, PP, RR, WW, PAIR_)                                                                 \
+#define LAUNCH_SM100_P(TT, PP, RR, WW, PAIR_, DD)                                                             \
   do {                                                                                                        \
-    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, kEmuPairs, PAIR_, WW>;                                      \
+    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, kEmuPairs, PAIR_, WW, DD>;                                  \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));   \
     MOJO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, q_map, k_map, v_map, p));                                      \
   } while (0)
 #define LAUNCH_SM100(TT, PP, RR, WW)                                                                          \
   do {                                                                                                        \
-    if (pair) LAUNCH_SM100_P(TT, PP, RR, WW, true); else LAUNCH_SM100_P(TT, PP, RR, WW, false);               \
+    if (a.head_dim == 64) LAUNCH_SM100_P(TT, PP, RR, WW, false, 64);                                          \
+    else if (pair) LAUNCH_SM100_P(TT, PP, RR, WW, true, 128);                                                 \
+    else LAUNCH_SM100_P(TT, PP, RR, WW, false, 128);                                                          \
   } while (0)
   // Three bodies reach this kernel: dense SDPA (non-causal, scores stay fp32), paged prefill (causal, scores stay
   // fp32) and the EXACT causal body: scores rounded to the input dtype as the golden's einsum materialises them

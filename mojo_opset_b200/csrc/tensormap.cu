@@ -116,7 +116,7 @@ int build_cache_map(const void* base, int dtype, int head_dim, int64_t block_siz
 }
 
 int build_tile_map(const void* base, int dtype, int64_t rows_per_block, int num_heads, int64_t num_blocks, int64_t s_b,
-                   int64_t s_h, int64_t s_t, int box_rows, CUtensorMap* out) {
+                   int64_t s_h, int64_t s_t, int box_rows, CUtensorMap* out, int halves) {
   TensorMapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
@@ -125,7 +125,7 @@ int build_tile_map(const void* base, int dtype, int64_t rows_per_block, int num_
   key.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
   key.dims[0] = 64;                        key.box[0] = 64;
   key.dims[1] = (uint64_t)rows_per_block;  key.strides[0] = (uint64_t)s_t * 2;  key.box[1] = (uint32_t)box_rows;
-  key.dims[2] = 2;                         key.strides[1] = 128;                key.box[2] = 1;
+  key.dims[2] = (uint64_t)halves;          key.strides[1] = 128;                key.box[2] = 1;
   key.dims[3] = (uint64_t)num_heads;       key.strides[2] = (uint64_t)s_h * 2;  key.box[3] = 1;
   key.dims[4] = (uint64_t)num_blocks;      key.strides[3] = (uint64_t)s_b * 2;  key.box[4] = 1;
   return get_tensor_map(key, out);

@@ -151,10 +151,10 @@ int build_cache_map(const void* base, int dtype, int head_dim, int64_t block_siz
                     CUtensorMap* out);
 
 
-// 5-D tensor map for the tcgen05 attention kernel (head_dim 128, 16-bit elements) over a [blocks, heads, rows, 128]
+// 5-D tensor map for the tcgen05 attention kernel (head_dim 64 * halves, 16-bit elements) over a [blocks, heads, rows, D]
 // tensor (element strides s_b, s_h, s_t): dims [64 | row | half | head | block], box = `box_rows` rows of ONE
 // 64-column half, 128-byte swizzle -> a box lands as [row][128 B], the K-major line layout UMMA reads.
 int build_tile_map(const void* base, int dtype, int64_t rows_per_block, int num_heads, int64_t num_blocks, int64_t s_b,
-                   int64_t s_h, int64_t s_t, int box_rows, CUtensorMap* out);
+                   int64_t s_h, int64_t s_t, int box_rows, CUtensorMap* out, int halves = 2);
 
 }  // namespace mojo

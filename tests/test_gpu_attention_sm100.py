@@ -297,8 +297,6 @@ def test_sdpa_attn_mask_vs_oracle(F, impl, kernel, shape):
     from oracle import golden
 
     B, Hq, Hkv, S, blk, D = shape
-    if kernel == "tcgen05" and D != 128:
-        pytest.skip("the tcgen05 kernel covers head_dim 128")
     g = torch.Generator().manual_seed(9)
     n = 2 * S
     q = torch.randn(B, Hq, n, D, generator=g).to(torch.bfloat16)
@@ -320,3 +318,27 @@ def test_sdpa_attn_mask_vs_oracle(F, impl, kernel, shape):
         torch.testing.assert_close(out_h.float(), ref_h.float(), **TOL)
     with pytest.raises(NotImplementedError):
         F.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), None, Hq != Hkv, torch.zeros(n, n, device=DEV))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_head_dim_64_on_tcgen05(F, impl, dtype):
+    """head_dim 64 (reference SDPA accepts {64, 128}; reference test test_attention.py:924-949 is 4q/2kv, 512 x 512, D 64)
+    on the tcgen05 kernel: dense SDPA with GQA, a cross-attention shape, ragged paged prefill with cached prefixes."""
+    from oracle import golden
+
+    g = torch.Generator().manual_seed(64)
+    impl("tcgen05")
+    for B, Hq, Hkv, Sq, Skv in ((1, 4, 2, 512, 512), (2, 3, 3, 700, 333), (1, 8, 2, 1025, 2048)):
+        q = (torch.randn(B, Sq, Hq, 64, generator=g) * 0.5).to(dtype).transpose(1, 2)
+        k = (torch.randn(B, Skv, Hkv, 64, generator=g) * 0.5).to(dtype).transpose(1, 2)
+        v = torch.randn(B, Skv, Hkv, 64, generator=g).to(dtype).transpose(1, 2)
+        ref = golden.sdpa(q, k, v, enable_gqa=Hq != Hkv)
+        out = F.sdpa(q.to(DEV), k.to(DEV), v.to(DEV), None, enable_gqa=Hq != Hkv)
+        torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)
+    for case in (([300, 513], [0, 77], 8, 2, 16, "AABB"), ([640], [1000], 4, 1, 128, "AABB"), ([257, 200], [3, 260], 4, 2, 32, "ABAB")):
+        q_lens, prefix, Hq, Hkv, bs, layout = case
+        q, kc, vc, cu_q, table, cu_kv = _paged_case(q_lens, prefix, Hq, Hkv, bs, dtype, seed=7, D=64)
+        ref = golden.paged_prefill_gqa(q, kc, vc, cu_q, table, None, cu_kv, layout)
+        out = F.paged_prefill_gqa(q.to(DEV), kc.to(DEV), vc.to(DEV), cu_q.to(DEV), table.to(DEV), None, cu_kv.to(DEV),
+                                  layout, max(q_lens), max(a + b for a, b in zip(q_lens, prefix)))
+        torch.testing.assert_close(out.cpu().float(), ref.float(), **TOL)

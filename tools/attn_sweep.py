@@ -56,6 +56,12 @@ def main():
                       for _ in range(3))
         cases[name] = (lambda qs=qs, ks=ks, vs=vs: F.sdpa(qs, ks, vs), 4 * Bd * H * S * S * D)
 
+    for name, Bd in (("sdpa d64 b2", 2), ("sdpa d64 b8", 8)):
+        H, S = 24, 4096
+        qs, ks, vs = (torch.empty(Bd, S, H, 64, dtype=torch.bfloat16, device=DEV).normal_().transpose(1, 2)
+                      for _ in range(3))
+        cases[name] = (lambda qs=qs, ks=ks, vs=vs: F.sdpa(qs, ks, vs), 4 * Bd * H * S * S * 64)
+
     # round-robin over the variants, several rounds, so that clock / power drift hits every variant alike;
     # report min and median over the rounds
     import statistics
