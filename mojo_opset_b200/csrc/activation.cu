@@ -65,7 +65,7 @@ template <typename T, bool GELU> __device__ __forceinline__ float unary_f(float 
 }
 
 template <typename T, bool GATED, bool CLAMP, bool GELU = false>
-__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 8 : 4) act_kernel(const T* __restrict__ gate, const T* __restrict__ up,
+__global__ void __launch_bounds__(256, 4) act_kernel(const T* __restrict__ gate, const T* __restrict__ up,
                                                   T* __restrict__ out, int64_t rows, int64_t cols, int64_t g_rs,
                                                   int64_t u_rs, int64_t o_rs, float limit) {
   constexpr int N = Vec16<T>::N;
@@ -74,12 +74,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 8 : 4) act_kernel(const 
     const T* g = gate + row * g_rs;
     const T* u = GATED ? up + row * u_rs : nullptr;
     T* o = out + row * o_rs;
-    // one vector per stream per thread and trip, plain loads: measured fastest (full occupancy beats unrolling,
-    // tools/microbench/stream3.cu: 6.8 TB/s at 32 registers vs 5.3 TB/s with four vectors in flight at 95)
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < vecs; v += (int64_t)gridDim.x * blockDim.x) {
-      const Vec16<T> gv = ld_vec(g + v * N);
-      Vec16<T> uv;
-      if (GATED) uv = ld_vec(u + v * N);
+    // Grid-stride over the row's vectors, TWO vectors in flight per thread and trip.  The math of these ops (two MUFU
+    // + ~10-18 FP instructions per element) makes them ISSUE-bound, not HBM-bound: with one vector per thread the
+    // ~100 instructions of per-thread set-up (64-bit index arithmetic) were 38 % of all instructions (ncu: 33.8 issued
+    // per element for GELU, 84 % issue utilisation, 0.58 of the HBM peak); a capped grid amortises them over ~20 vectors.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto compute = [&](const Vec16<T>& gv, const Vec16<T>& uv) {
       Vec16<T> ov;
 #pragma unroll
       for (int e = 0; e < N; ++e) {
@@ -92,7 +92,24 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 8 : 4) act_kernel(const 
           ov.v[e] = DType<T>::from_f(unary_f<T, GELU>(gf));
         }
       }
-      st_vec(o + v * N, ov);
+      return ov;
+    };
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + stride < vecs; v += 2 * stride) {
+      const Vec16<T> g0 = ld_vec(g + v * N), g1 = ld_vec(g + (v + stride) * N);
+      Vec16<T> u0, u1;
+      if (GATED) {
+        u0 = ld_vec(u + v * N);
+        u1 = ld_vec(u + (v + stride) * N);
+      }
+      st_vec(o + v * N, compute(g0, u0));
+      st_vec(o + (v + stride) * N, compute(g1, u1));
+    }
+    if (v < vecs) {
+      const Vec16<T> g0 = ld_vec(g + v * N);
+      Vec16<T> u0;
+      if (GATED) u0 = ld_vec(u + v * N);
+      st_vec(o + v * N, compute(g0, u0));
     }
     // scalar tail when cols is not a multiple of the vector width
     for (int64_t c = vecs * N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols;
@@ -145,6 +162,12 @@ static int act_entry(const void* gate, const void* up, void* out, int64_t rows, 
   int64_t gx = (per_row + 255) / 256;
   gx = gx < 1 ? 1 : (gx > 0x7fffffffLL ? 0x7fffffffLL : gx);
   int64_t gy = rows < 1 ? 1 : (rows > 65535 ? 65535 : rows);
+  // the vector kernel strides over its row: at most ~2 resident waves of blocks in all (8 blocks of 256 threads per SM)
+  if (vec_ok) {
+    const int64_t cap = (int64_t)kNumSMs * 4 * 4;  // 4 resident blocks per SM, 4 waves
+    const int64_t gx_cap = (cap + gy - 1) / gy;
+    if (gx > gx_cap) gx = gx_cap < 1 ? 1 : gx_cap;
+  }
   dim3 grid((unsigned)gx, (unsigned)gy);
   return dispatch_dtype(dtype, [&](auto tag) {
     using T = decltype(tag);

@@ -27,68 +27,74 @@ __global__ void __launch_bounds__(TPR > kLnCta ? TPR : kLnCta) layernorm_kernel(
   const int vecs = hidden / VEC;
   __shared__ float part[2][32];
 
-  auto group_sum = [&](float v, int which) -> float {
+  // both moments in ONE reduction round: the sums are taken of d = x - x0 (x0 = the row's first element), so
+  // var = E[d^2] - E[d]^2 does not cancel for rows that sit far from zero, and the second pass over the registers with
+  // its second block-level reduction (a barrier + shared-memory round trip: the kernel is latency-, not bandwidth-bound
+  // there) is gone
+  auto group_sum2 = [&](float2 v) -> float2 {
     if constexpr (TPR <= 32) {
 #pragma unroll
-      for (int o = TPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      for (int o = TPR / 2; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+      }
       return v;
     } else {
-      v = warp_sum(v);
-      if ((threadIdx.x & 31) == 0) part[which][threadIdx.x >> 5] = v;
+      v.x = warp_sum(v.x);
+      v.y = warp_sum(v.y);
+      if ((threadIdx.x & 31) == 0) {
+        part[0][threadIdx.x >> 5] = v.x;
+        part[1][threadIdx.x >> 5] = v.y;
+      }
       __syncthreads();
       constexpr int WPR = TPR / 32;
       const int w0 = (threadIdx.x / TPR) * WPR;
-      float t = 0.f;
+      float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < WPR; ++i) t += part[which][w0 + i];
+      for (int i = 0; i < WPR; ++i) {
+        t.x += part[0][w0 + i];
+        t.y += part[1][w0 + i];
+      }
       return t;
     }
   };
 
   LnPack<T, VEC> keep[kLnPacks];
-  float s = 0.f;
+  float s = 0.f, ss = 0.f, x0 = 0.f;
   if (active) {
     const T* xr = x + row * x_rs;
+    x0 = DType<T>::to_f(xr[0]);
 #pragma unroll
     for (int i = 0; i < kLnPacks; ++i) {
       const int v = lane_in_row + i * TPR;
-      if (v < vecs) {
-        keep[i] = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) s += DType<T>::to_f(keep[i].v[e]);
-      }
+      if (v < vecs) keep[i] = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
     }
-    for (int v = lane_in_row + kLnPacks * TPR; v < vecs; v += TPR) {  // rows wider than the register slice
-      const LnPack<T, VEC> a = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) s += DType<T>::to_f(a.v[e]);
-    }
-  }
-  const float mean = group_sum(s, 0) / (float)hidden;
-  float ss = 0.f;
-  if (active) {
-    const T* xr = x + row * x_rs;
 #pragma unroll
     for (int i = 0; i < kLnPacks; ++i) {
       const int v = lane_in_row + i * TPR;
       if (v < vecs) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          const float d = DType<T>::to_f(keep[i].v[e]) - mean;
+          const float d = DType<T>::to_f(keep[i].v[e]) - x0;
+          s += d;
           ss = fmaf(d, d, ss);
         }
       }
     }
-    for (int v = lane_in_row + kLnPacks * TPR; v < vecs; v += TPR) {
+    for (int v = lane_in_row + kLnPacks * TPR; v < vecs; v += TPR) {  // rows wider than the register slice
       const LnPack<T, VEC> a = *reinterpret_cast<const LnPack<T, VEC>*>(xr + (int64_t)v * VEC);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const float d = DType<T>::to_f(a.v[e]) - mean;
+        const float d = DType<T>::to_f(a.v[e]) - x0;
+        s += d;
         ss = fmaf(d, d, ss);
       }
     }
   }
-  const float var = group_sum(ss, 1) / (float)hidden;
+  const float2 mom = group_sum2(make_float2(s, ss));
+  const float dmean = mom.x / (float)hidden;
+  const float mean = x0 + dmean;
+  const float var = fmaxf(mom.y / (float)hidden - dmean * dmean, 0.f);
   if (!active) return;
   const float inv = __fdiv_rn(1.0f, __fsqrt_rn(var + eps));
   T* yr = y + row * y_rs;

@@ -16,7 +16,9 @@
 // RoPE multiplies in promote(T, cos dtype) with each product and the sum rounded separately
 // (position_embedding.py:128-129), K/V are moved bit-exactly.
 //
-// One CTA (256 threads) per token.  A head row (D elements) is owned by D/8 consecutive lanes, 8 elements
+// One CTA (128 threads) per token (ncu, T = 8192 at Qwen3 shapes: the kernel is ISSUE-bound - 3.15 instructions per
+// cycle, 32 issued per element, two thirds of them per-thread set-up and per-trip bookkeeping - so a thread now owns
+// six head rows instead of three, one thread looks the page slot up for the CTA, and the norm weights are unpacked once).  A head row (D elements) is owned by D/8 consecutive lanes, 8 elements
 // (16 bytes) per lane: the sum of squares is a shuffle reduction inside the lane group, the RoPE partner half sits
 // rope_dim/16 lanes away (one shuffle of the packed row).  cos/sin slices are loaded once per thread.
 #include <type_traits>
@@ -69,10 +71,13 @@ template <typename T> __device__ __forceinline__ Row8 pack8(const float (&f)[8])
 }
 
 // LPH = lanes per head = D / 8; C = cos/sin element type (float or T); NORM: apply the per-head RMSNorm
+constexpr int kNrsThreads = 128;
+
 template <typename T, typename C, int LPH, bool NORM>
-__global__ void __launch_bounds__(256, 5) norm_rope_store_kernel(const NrsArgs a) {
+__global__ void __launch_bounds__(kNrsThreads, 5) norm_rope_store_kernel(const NrsArgs a) {
   constexpr int D = LPH * 8;
-  constexpr int HSLOTS = 256 / LPH;
+  constexpr int HSLOTS = kNrsThreads / LPH;
+  __shared__ int64_t s_slot[2];
   constexpr bool ROUND_T = std::is_same<T, C>::value;  // intermediates of a same-dtype RoPE are rounded to T
   const int64_t tok = blockIdx.x;
   const int sl = threadIdx.x % LPH, hs = threadIdx.x / LPH;
@@ -95,38 +100,41 @@ __global__ void __launch_bounds__(256, 5) norm_rope_store_kernel(const NrsArgs a
       sn[i] = DType<C>::to_f(sv.v[i]);
     }
   }
-  Row8 wq_p = {{0u, 0u, 0u, 0u}}, wk_p = wq_p;  // norm weights stay packed (registers) until used
+  float wqf[8], wkf[8];  // this lane's slices of the two norm weights, unpacked once
   if (NORM) {
-    wq_p = *reinterpret_cast<const Row8*>((const T*)a.wq + e0);
-    wk_p = *reinterpret_cast<const Row8*>((const T*)a.wk + e0);
+    unpack8<T>(*reinterpret_cast<const Row8*>((const T*)a.wq + e0), wqf);
+    unpack8<T>(*reinterpret_cast<const Row8*>((const T*)a.wk + e0), wkf);
   }
 
-  // ---- the rows of the first kPre trips are requested BEFORE the page-slot lookup below: that lookup is a chain of
-  // four to eight dependent loads (binary search over cu_q_lens, context length, block table) and a CTA only lives
-  // for three trips at Qwen3 shapes, so with the rows issued after it about half of a CTA's life was lookup latency
-  // (prefill T = 8192: 67 us = 0.47 of the HBM peak)
-  const int total = a.hq + 2 * a.hkv;
-  constexpr int kPre = 3;
-  auto head_src = [&](int h, int& kind, int& hh) -> const T* {
-    kind = h >= total ? 2 : h < a.hq ? 0 : (h < a.hq + a.hkv ? 1 : 2);  // 0: q head, 1: k head, 2: v head / idle
-    hh = kind == 0 ? h : (h < a.hq + a.hkv ? h - a.hq : h - a.hq - a.hkv);
-    return kind == 0 ? (const T*)a.q + tok * a.q_t + (int64_t)hh * a.q_h
-         : kind == 1 ? (const T*)a.k + tok * a.k_t + (int64_t)hh * a.k_h
-                     : (const T*)a.v + tok * a.v_t + (int64_t)hh * a.v_h;
-  };
-  Row8 pre[kPre];
+  // ---- three plain loops - q heads, k heads, v heads - each with its own bumped pointers (the first version walked
+  // one mixed head list: per trip ~300 instructions of kind selects and 64-bit address arithmetic for 8 elements per
+  // thread - ncu: 32 instructions issued per element, the kernel issue-bound at 0.59 of the HBM peak).  The rows of
+  // the first trips are requested BEFORE the page-slot lookup: that lookup is a chain of four to eight dependent loads.
+  const int64_t hstep = HSLOTS;
+  const T* qp = (const T*)a.q + tok * a.q_t + (int64_t)hs * a.q_h + e0;
+  const T* kp = (const T*)a.k + tok * a.k_t + (int64_t)hs * a.k_h + e0;
+  const T* vp = (const T*)a.v + tok * a.v_t + (int64_t)hs * a.v_h + e0;
+  constexpr int kPreQ = 4, kPreKV = 1;  // Qwen3 / Llama shapes at head_dim 128: the whole token (12 KB) in flight
+  Row8 pre_q[kPreQ], pre_k[kPreKV], pre_v[kPreKV];
 #pragma unroll
-  for (int i = 0; i < kPre; ++i) {
-    pre[i] = Row8{{0u, 0u, 0u, 0u}};
-    int kind, hh;
-    const int h = i * HSLOTS + hs;
-    const T* src = head_src(h, kind, hh);
-    if (h < total) pre[i] = *reinterpret_cast<const Row8*>(src + e0);
+  for (int i = 0; i < kPreQ; ++i) {
+    pre_q[i] = Row8{{0u, 0u, 0u, 0u}};
+    if (i * HSLOTS + hs < a.hq) pre_q[i] = *reinterpret_cast<const Row8*>(qp + i * hstep * a.q_h);
+  }
+#pragma unroll
+  for (int i = 0; i < kPreKV; ++i) {
+    pre_k[i] = Row8{{0u, 0u, 0u, 0u}};
+    pre_v[i] = pre_k[i];
+    if (i * HSLOTS + hs < a.hkv) {
+      pre_k[i] = *reinterpret_cast<const Row8*>(kp + i * hstep * a.k_h);
+      pre_v[i] = *reinterpret_cast<const Row8*>(vp + i * hstep * a.v_h);
+    }
   }
 
-  // ---- page slot of this token (warp-uniform; every thread computes it, a handful of cached loads)
-  int64_t kc_off = -1, vc_off = -1;
-  {
+  // ---- page slot of this token: ONE thread walks cu_q_lens / context lengths / block table while the others' row
+  // loads are in flight and the q heads are processed; the barrier that publishes it sits in front of the k heads
+  if (threadIdx.x == 0) {
+    int64_t kc_off = -1, vc_off = -1;
     int seq = -1, pos = -1;
     if (a.cu_q == nullptr) {  // decode: token i is sequence i at position context_i
       if (tok < a.num_seqs) {
@@ -158,18 +166,14 @@ __global__ void __launch_bounds__(256, 5) norm_rope_store_kernel(const NrsArgs a
         }
       }
     }
+    s_slot[0] = kc_off;
+    s_slot[1] = vc_off;
   }
 
-  auto process = [&](int h0, const Row8* fetched) {
-    const int h = h0 + hs;
-    const bool active = h < total;
-    int kind, hh;
-    const T* src = head_src(h, kind, hh);
-    Row8 row = {{0u, 0u, 0u, 0u}};
-    if (fetched) row = *fetched; else if (active) row = *reinterpret_cast<const Row8*>(src + e0);
-    if (active && kind == 2 && vc_off >= 0)
-      *reinterpret_cast<Row8*>((T*)a.vc + vc_off + (int64_t)hh * a.vc_h + e0) = row;
-    // a warp holds 32 / LPH heads that may be of different kinds: the shuffles below are executed by all lanes
+  const int lane = threadIdx.x & 31;
+  const int src_lane = lane - sl + (rotary ? partner_lane : sl);
+  // RMSNorm over the head (lane group) + RoPE of one packed row; executed by every lane of the warp (shuffles)
+  auto norm_rope = [&](Row8 row, const float (&wf)[8]) -> Row8 {
     float x[8];
     unpack8<T>(row, x);
     if (NORM) {
@@ -178,26 +182,19 @@ __global__ void __launch_bounds__(256, 5) norm_rope_store_kernel(const NrsArgs a
       for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
 #pragma unroll
       for (int o = LPH / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      // MUFU reciprocal square root (<= 2 ulp of fp32; D is a power of two, so the mean is exact): the IEEE
-      // division + square root of the stand-alone norm kernel cost ~80 instructions per head here
+      // MUFU reciprocal square root (<= 2 ulp of fp32; D is a power of two, so the mean is exact)
       const float inv = rsqrtf(__fmaf_rn(ss, 1.0f / (float)D, a.eps));
-      float w[8];
-      unpack8<T>(kind == 0 ? wq_p : wk_p, w);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = __fmul_rn(__fmul_rn(x[i], inv), w[i]);
+      for (int i = 0; i < 8; ++i) x[i] = __fmul_rn(__fmul_rn(x[i], inv), wf[i]);
       row = pack8<T>(x);  // the norm's output is materialised in T
       unpack8<T>(row, x);
     }
-    // partner half of the (normalised) row: lane (sl +- half/8) of the same head
-    Row8 other;
-    const int src_lane = (threadIdx.x & 31) - sl + (rotary ? partner_lane : sl);
+    Row8 other;  // partner half of the (normalised) row: lane (sl +- half/8) of the same head
 #pragma unroll
     for (int i = 0; i < 4; ++i) other.w[i] = __shfl_sync(0xffffffffu, row.w[i], src_lane);
-    if (kind == 2) return;
     if (rotary) {
-      float y[8];
+      float y[8], o[8];
       unpack8<T>(other, y);
-      float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         // rotate_half(x) = cat(-x2, x1): the partner enters negated in the first half only
@@ -210,18 +207,50 @@ __global__ void __launch_bounds__(256, 5) norm_rope_store_kernel(const NrsArgs a
       }
       row = pack8<T>(o);
     }
-    if (kind == 0) {
-      *reinterpret_cast<Row8*>((T*)a.q_out + tok * a.qo_t + (int64_t)hh * a.qo_h + e0) = row;
-    } else {
-      if (kc_off >= 0) *reinterpret_cast<Row8*>((T*)a.kc + kc_off + (int64_t)hh * a.kc_h + e0) = row;
-      if (a.k_out) *reinterpret_cast<Row8*>((T*)a.k_out + tok * a.ko_t + (int64_t)hh * a.ko_h + e0) = row;
-    }
+    return row;
   };
-  // every lane of a warp runs every trip (the shuffles inside are full-warp); lanes past the last head idle as "v"
+
+  // ---- q heads
+  T* qo = (T*)a.q_out + tok * a.qo_t + (int64_t)hs * a.qo_h + e0;
 #pragma unroll
-  for (int i = 0; i < kPre; ++i)
-    if (i * HSLOTS < total) process(i * HSLOTS, &pre[i]);
-  for (int h0 = kPre * HSLOTS; h0 < total; h0 += HSLOTS) process(h0, nullptr);
+  for (int i = 0; i < kPreQ; ++i) {
+    if (i * HSLOTS < a.hq) {  // (uniform over the CTA; every lane of a warp runs the shuffles)
+      const Row8 r = norm_rope(pre_q[i], wqf);
+      if (i * HSLOTS + hs < a.hq) *reinterpret_cast<Row8*>(qo + i * hstep * a.qo_h) = r;
+    }
+  }
+  for (int h0 = kPreQ * HSLOTS; h0 < a.hq; h0 += HSLOTS) {
+    const bool active = h0 + hs < a.hq;
+    Row8 row = {{0u, 0u, 0u, 0u}};
+    if (active) row = *reinterpret_cast<const Row8*>(qp + (int64_t)h0 * a.q_h);
+    const Row8 r = norm_rope(row, wqf);
+    if (active) *reinterpret_cast<Row8*>(qo + (int64_t)h0 * a.qo_h) = r;
+  }
+
+  __syncthreads();
+  const int64_t kc_off = s_slot[0], vc_off = s_slot[1];
+
+  // ---- k heads -> key_cache slot (and k_out), v heads -> value_cache slot (pure copy)
+  T* kc_p = (T*)a.kc + kc_off + (int64_t)hs * a.kc_h + e0;
+  T* vc_p = (T*)a.vc + vc_off + (int64_t)hs * a.vc_h + e0;
+  T* ko = a.k_out ? (T*)a.k_out + tok * a.ko_t + (int64_t)hs * a.ko_h + e0 : nullptr;
+  for (int h0 = 0; h0 < a.hkv; h0 += HSLOTS) {
+    const bool active = h0 + hs < a.hkv;
+    Row8 krow = {{0u, 0u, 0u, 0u}}, vrow = krow;
+    if (h0 < kPreKV * HSLOTS) {
+      krow = pre_k[0];
+      vrow = pre_v[0];
+    } else if (active) {
+      krow = *reinterpret_cast<const Row8*>(kp + (int64_t)h0 * a.k_h);
+      vrow = *reinterpret_cast<const Row8*>(vp + (int64_t)h0 * a.v_h);
+    }
+    const Row8 r = norm_rope(krow, wkf);
+    if (active) {
+      if (kc_off >= 0) *reinterpret_cast<Row8*>(kc_p + (int64_t)h0 * a.kc_h) = r;
+      if (ko) *reinterpret_cast<Row8*>(ko + (int64_t)h0 * a.ko_h) = r;
+      if (vc_off >= 0) *reinterpret_cast<Row8*>(vc_p + (int64_t)h0 * a.vc_h) = vrow;
+    }
+  }
 }
 
 }  // namespace mojo
@@ -285,8 +314,8 @@ extern "C" int mojo_b200_norm_rope_store_kv(
   const bool cos_f32 = cos_dtype == MOJO_B200_F32;
 #define NRS_LAUNCH(TT, CC, LL)                                                                \
   do {                                                                                        \
-    if (norm) norm_rope_store_kernel<TT, CC, LL, true><<<grid, 256, 0, s>>>(a);               \
-    else norm_rope_store_kernel<TT, CC, LL, false><<<grid, 256, 0, s>>>(a);                   \
+    if (norm) norm_rope_store_kernel<TT, CC, LL, true><<<grid, kNrsThreads, 0, s>>>(a);       \
+    else norm_rope_store_kernel<TT, CC, LL, false><<<grid, kNrsThreads, 0, s>>>(a);           \
   } while (0)
 #define NRS_DIM(TT, CC)                                        \
   do {                                                         \

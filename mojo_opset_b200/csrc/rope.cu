@@ -10,6 +10,8 @@
 // Rounding follows the eager golden: math in promote(T, cos dtype); each product and the sum are rounded
 // separately (no FMA contraction); when cos has the same 16-bit dtype as q the intermediates are rounded
 // to that dtype too.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mojo {
@@ -64,6 +66,7 @@ struct RopeArgs {
   const void *q, *k, *cos, *sin;
   void *qo, *ko;
   int64_t seq;
+  int64_t tokens;  // batch * seq (the slice kernel strides over them)
   int q_heads, k_heads, head_dim, rope_dim;
   int64_t q_b, q_s, q_h, k_b, k_s, k_h, qo_b, qo_s, qo_h, ko_b, ko_s, ko_h, cos_b, cos_s;
 };
@@ -91,17 +94,20 @@ __global__ void __launch_bounds__(256) apply_rope_kernel(const RopeArgs a) {
 // is loaded by two threads of the same warp instruction (one L1 request).  No integer division in the loop.
 // Requires SLICES = head_dim / VEC to be a power of two <= 32.
 template <typename T, typename C, int VEC, bool ROUND_T, int SLICES>
-__global__ void __launch_bounds__(256, 6) apply_rope_slice_kernel(const RopeArgs a) {
+__global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs a) {
   constexpr int HSLOTS = 256 / SLICES;
-  const uint32_t tok = blockIdx.x;
-  const uint32_t b = tok / (uint32_t)a.seq;
-  const uint32_t s = tok - b * (uint32_t)a.seq;
   const int sl = threadIdx.x % SLICES, hs = threadIdx.x / SLICES;
   const int nope = a.head_dim - a.rope_dim, half = a.rope_dim / 2;
   const int off = sl * VEC;  // this thread's output slice inside a head
   const bool rotary = off >= nope;
   const bool second = off >= nope + half;
   const int partner = second ? off - half : off + half;
+  // a CTA strides over tokens (the grid is capped at a few resident waves: thousands of 10 KB CTAs spent their lives
+  // in launch and first-load latency)
+#pragma unroll 1
+  for (uint32_t tok = blockIdx.x; tok < (uint32_t)a.tokens; tok += gridDim.x) {
+  const uint32_t b = tok / (uint32_t)a.seq;
+  const uint32_t s = tok - b * (uint32_t)a.seq;
   const T* qs = (const T*)a.q + (int64_t)b * a.q_b + (int64_t)s * a.q_s;
   const T* ks = (const T*)a.k + (int64_t)b * a.k_b + (int64_t)s * a.k_s - (int64_t)a.q_heads * a.k_h;
   T* qd = (T*)a.qo + (int64_t)b * a.qo_b + (int64_t)s * a.qo_s;
@@ -113,33 +119,109 @@ __global__ void __launch_bounds__(256, 6) apply_rope_slice_kernel(const RopeArgs
     cs = *reinterpret_cast<const Pack<C, VEC>*>((const C*)a.cos + row);
     sn = *reinterpret_cast<const Pack<C, VEC>*>((const C*)a.sin + row);
   }
+  // The first kRopeTrips head rows of a thread are all requested before any is rotated (one dependent load per trip made
+  // the kernel latency-bound: 0.71 of the HBM peak at T = 8192), and the partner slice comes from the partner lane
+  // (same head, rope_dim/2 elements away = a fixed lane distance inside the warp) by shuffle instead of a second load.
+  constexpr int kRopeTrips = 3;
+  constexpr int kWords = VEC * (int)sizeof(T) / 4;
+  static_assert(kWords >= 1, "slices are at least one word");
+  const int partner_lane = (int)(threadIdx.x & 31u) + (second ? -(half / VEC) : (half / VEC));
+  // cos / sin of this thread's slice as fp32, the sign of rotate_half folded into sin once (rotate_half(x) =
+  // cat(-x2, x1): the partner enters negated in the first half only; (-y) * s == y * (-s) exactly)
+  float csf[VEC], snf[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    csf[e] = rotary ? DType<C>::to_f(cs.v[e]) : 0.f;
+    snf[e] = rotary ? (second ? DType<C>::to_f(sn.v[e]) : -DType<C>::to_f(sn.v[e])) : 0.f;
+  }
+  // 16-bit pairs are unpacked word-wise (bf16: one shift / one mask per element; element-wise conversions of the packed
+  // struct compiled to a PRMT extract + a shift each - ncu: 22 instructions issued per element, ALU pipe 56 %)
+  auto unpack = [&](const Pack<T, VEC>& pk, float (&f)[VEC]) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value && VEC % 2 == 0) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) f[e] = DType<T>::to_f(pk.v[e]);
+    }
+  };
+  auto rotate = [&](Pack<T, VEC>& o, const Pack<T, VEC>& xb) {
+    float x[VEC], y[VEC], r[VEC];
+    unpack(o, x);
+    unpack(xb, y);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float p = __fmul_rn(x[e], csf[e]), q = __fmul_rn(y[e], snf[e]);
+      if (ROUND_T) {
+        p = round_through<T>(p);
+        q = round_through<T>(q);
+      }
+      r[e] = __fadd_rn(p, q);
+    }
+    if constexpr (sizeof(T) == 2 && VEC % 2 == 0) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          const __nv_bfloat162 t = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+          w[i] = *reinterpret_cast<const uint32_t*>(&t);
+        } else {
+          const __half2 t = __floats2half2_rn(r[2 * i], r[2 * i + 1]);
+          w[i] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o.v[e] = DType<T>::from_f(r[e]);
+    }
+  };
+  Pack<T, VEC> pre[kRopeTrips];
+#pragma unroll
+  for (int i = 0; i < kRopeTrips; ++i) {
+    const int h = hs + i * HSLOTS;
+    const T* src = h < a.q_heads ? qs + (int64_t)h * a.q_h : ks + (int64_t)h * a.k_h;
+    if (h < total) pre[i] = *reinterpret_cast<const Pack<T, VEC>*>(src + off);
+    else memset(&pre[i], 0, sizeof(pre[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < kRopeTrips; ++i) {
+    const int h = hs + i * HSLOTS;
+    Pack<T, VEC> xb;
+    {  // every lane of the warp takes part in the exchange (heads of one warp may straddle `total`)
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&pre[i]);
+      uint32_t* d = reinterpret_cast<uint32_t*>(&xb);
+#pragma unroll
+      for (int k = 0; k < kWords; ++k) d[k] = __shfl_sync(0xffffffffu, w[k], rotary ? partner_lane : (int)(threadIdx.x & 31u));
+    }
+    if (h < total) {
+      T* dst = h < a.q_heads ? qd + (int64_t)h * a.qo_h : kd + (int64_t)h * a.ko_h;
+      if (rotary) rotate(pre[i], xb);
+      *reinterpret_cast<Pack<T, VEC>*>(dst + off) = pre[i];
+    }
+  }
 #pragma unroll 1
-  for (int h = hs; h < total; h += HSLOTS) {
+  for (int h = hs + kRopeTrips * HSLOTS; h < total; h += HSLOTS) {
     const T* src = h < a.q_heads ? qs + (int64_t)h * a.q_h : ks + (int64_t)h * a.k_h;
     T* dst = h < a.q_heads ? qd + (int64_t)h * a.qo_h : kd + (int64_t)h * a.ko_h;
     Pack<T, VEC> o = *reinterpret_cast<const Pack<T, VEC>*>(src + off);
     if (rotary) {
       const Pack<T, VEC> xb = *reinterpret_cast<const Pack<T, VEC>*>(src + partner);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const float x = DType<T>::to_f(o.v[e]), y = DType<T>::to_f(xb.v[e]);
-        // rotate_half(x) = cat(-x2, x1): the partner enters negated in the first half only
-        float p = __fmul_rn(x, DType<C>::to_f(cs.v[e])), q = __fmul_rn(second ? y : -y, DType<C>::to_f(sn.v[e]));
-        if (ROUND_T) {
-          p = round_through<T>(p);
-          q = round_through<T>(q);
-        }
-        o.v[e] = DType<T>::from_f(__fadd_rn(p, q));
-      }
+      rotate(o, xb);
     }
     *reinterpret_cast<Pack<T, VEC>*>(dst + off) = o;
   }
+  }  // token loop
 }
 
 template <typename T, typename C, int VEC, bool ROUND_T>
 static bool launch_rope_fast(const RopeArgs& a, int64_t tokens, cudaStream_t s) {
   if (a.head_dim % VEC) return false;
-  const unsigned grid = (unsigned)tokens;
+  const int64_t cap = (int64_t)kNumSMs * 4 * 3;
+  const unsigned grid = (unsigned)(tokens < cap ? tokens : cap);
   switch (a.head_dim / VEC) {
     case 8: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 8><<<grid, 256, 0, s>>>(a); return true;
     case 16: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 16><<<grid, 256, 0, s>>>(a); return true;
@@ -236,7 +318,7 @@ extern "C" int mojo_b200_apply_rope(const void* q, const void* k, const void* co
   MOJO_REQUIRE(tokens <= 0x7fffffffLL, MOJO_B200_EUNSUPPORTED, "apply_rope: too many tokens");
   MOJO_REQUIRE(dtype >= 0 && dtype <= 2 && cos_dtype >= 0 && cos_dtype <= 2, MOJO_B200_EINVAL, "apply_rope: bad dtype");
 
-  RopeArgs a{q, k, cos, sin, q_out, k_out, seq, q_heads, k_heads, head_dim, rope_dim,
+  RopeArgs a{q, k, cos, sin, q_out, k_out, seq, tokens, q_heads, k_heads, head_dim, rope_dim,
              q_stride_b, q_stride_s, q_stride_h, k_stride_b, k_stride_s, k_stride_h,
              qo_stride_b, qo_stride_s, qo_stride_h, ko_stride_b, ko_stride_s, ko_stride_h, cos_stride_b, cos_stride_s};
 

@@ -77,6 +77,25 @@ __global__ void __launch_bounds__(128) store_table_kernel(
     const int32_t* __restrict__ ctx_lens, int num_seqs, int64_t num_tokens, int num_kv_heads, int row_bytes,
     int64_t num_blocks, int block_size, StoreStrides st) {
   const int64_t tok = blockIdx.x;
+  // The token's rows are requested BEFORE its page slot is looked up: the lookup is a chain of four to six dependent
+  // loads (binary search over cu_q_lens, context length, block table) and a CTA moves only 4 KB, so with the rows
+  // issued after it the CTA's life was almost all lookup latency (0.70 of the HBM peak at T = 8192).
+  using V = typename BytesVec<VB>::type;
+  const int vecs_per_row = row_bytes / VB;
+  const int total = num_kv_heads * vecs_per_row;
+  constexpr int kPre = 2;
+  V pk[kPre], pv[kPre];
+  const char* ks0 = ks + tok * st.ks_t;
+  const char* vs0 = vs + tok * st.vs_t;
+#pragma unroll
+  for (int t = 0; t < kPre; ++t) {
+    const int i = threadIdx.x + t * blockDim.x;
+    if (i < total) {
+      const int h = i / vecs_per_row, c = i - h * vecs_per_row;
+      pk[t] = *reinterpret_cast<const V*>(ks0 + h * st.ks_h + (int64_t)c * VB);
+      pv[t] = *reinterpret_cast<const V*>(vs0 + h * st.vs_h + (int64_t)c * VB);
+    }
+  }
   int seq, pos;
   if (cu_q == nullptr) {  // decode: token i belongs to sequence i at position context_i
     if (tok >= num_seqs) return;
@@ -101,9 +120,19 @@ __global__ void __launch_bounds__(128) store_table_kernel(
   const int blk = table[seq * table_stride + logical];
   if (blk < 0 || blk >= num_blocks) return;
   const int off = pos - logical * block_size;
-  copy_token_heads<VB>(ks + tok * st.ks_t, vs + tok * st.vs_t, kc + (int64_t)blk * st.kc_b + (int64_t)off * st.kc_t,
-                       vc + (int64_t)blk * st.vc_b + (int64_t)off * st.vc_t, num_kv_heads, row_bytes / VB, st.ks_h,
-                       st.vs_h, st.kc_h, st.vc_h, threadIdx.x, blockDim.x);
+  char* kc0 = kc + (int64_t)blk * st.kc_b + (int64_t)off * st.kc_t;
+  char* vc0 = vc + (int64_t)blk * st.vc_b + (int64_t)off * st.vc_t;
+#pragma unroll
+  for (int t = 0; t < kPre; ++t) {
+    const int i = threadIdx.x + t * blockDim.x;
+    if (i < total) {
+      const int h = i / vecs_per_row, c = i - h * vecs_per_row;
+      *reinterpret_cast<V*>(kc0 + h * st.kc_h + (int64_t)c * VB) = pk[t];
+      *reinterpret_cast<V*>(vc0 + h * st.vc_h + (int64_t)c * VB) = pv[t];
+    }
+  }
+  copy_token_heads<VB>(ks0, vs0, kc0, vc0, num_kv_heads, vecs_per_row, st.ks_h, st.vs_h, st.kc_h, st.vc_h,
+                       threadIdx.x + kPre * blockDim.x, blockDim.x);
 }
 
 static int pick_vec_bytes(int row_bytes, const StoreStrides& s, const void* a, const void* b, const void* c,
