@@ -655,6 +655,15 @@ def run_extra(m, dev, peaks, args):
                     "ms": ms, "ms_best": ms_best, "tflops": flops / ms / 1e9, "tflops_best": flops / ms_best / 1e9,
                     "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"], "flops": flops}
         del qs, ks, vs
+    # head_dim 64 (reference SDPA accepts {64, 128}) on the same tcgen05 kernel: exponentials per FLOP double
+    qs, ks, vs = (torch.empty(2, S, H, 64, dtype=torch.bfloat16, device=dev).normal_().transpose(1, 2) for _ in range(3))
+    ms, ms_best = _time_gpu_burst(lambda: sdpa(qs, ks, vs), 10)
+    flops = 4 * 2 * H * S * S * 64
+    out["sdpa_d64"] = {"workload": "MojoSdpa 24 heads hd64 S=4096 non-causal bf16, batch 2", "ms": ms, "ms_best": ms_best,
+                       "tflops": flops / ms / 1e9, "tflops_best": flops / ms_best / 1e9,
+                       "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"], "flops": flops}
+    del qs, ks, vs
+    out["decode_small"] = run_decode_small(m, dev, peaks)
     if args.sustain_s > 0:
         ms, flops = out["prefill_cfg3"]["ms"], out["prefill_cfg3"]["flops"]
         iters = max(10, int(2.0 * args.sustain_s * 1e3 / ms))
@@ -663,6 +672,45 @@ def run_extra(m, dev, peaks, args):
         out["prefill_cfg3"]["sustained"] = {"seconds": ms_s * iters * 1e-3, "launches": iters, "ms": ms_s,
                                             "tflops": flops / ms_s / 1e9, "peak_sustained": sus_peak,
                                             "frac_of_bf16_sustained_peak": flops / ms_s / 1e9 / sus_peak}
+    return out
+
+
+def run_decode_small(m, dev, peaks):
+    """Small-batch split-KV decode (the batch-1 / batch-4 serving cases): 20 launches replayed from one CUDA graph."""
+    out = {}
+    decode = m.MojoPagedDecodeGQA()
+    Hq, Hkv, D, bs = 32, 8, 128, 16
+    for name, B, ctx in (("b1_ctx32k", 1, 32768), ("b4_ctx8k", 4, 8192)):
+        nb = B * ctx // bs + 10
+        kc = torch.empty(nb, Hkv, bs, D, dtype=torch.bfloat16, device=dev).normal_()
+        vc = torch.empty(nb, Hkv, bs, D, dtype=torch.bfloat16, device=dev).normal_()
+        q = torch.empty(B, Hq, D, dtype=torch.bfloat16, device=dev).normal_()
+        table = torch.randperm(nb)[: B * ctx // bs].view(B, -1).to(torch.int32).to(dev)
+        lens = torch.full((B,), ctx, dtype=torch.int32, device=dev)
+        fn = lambda: decode(q, kc, vc, lens, table, max_total_seq_len=ctx)  # noqa: E731
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                fn()
+        graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(3):
+            a.record()
+            graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) / 20)
+        nbytes = decode_bytes(B, ctx, Hq, Hkv, D, bs)
+        gbs = nbytes / best / 1e6
+        out[name] = {"workload": f"MojoPagedDecodeGQA batch {B}, 32q/8kv hd128 page16 ctx {ctx} bf16 (split-KV)",
+                     "us": best * 1e3, "gbs": gbs, "frac_of_measured_hbm": gbs / peaks["hbm_gbs"],
+                     "algorithmic_bytes": nbytes}
+        del kc, vc
     return out
 
 
