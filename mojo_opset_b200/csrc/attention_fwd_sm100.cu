@@ -48,7 +48,6 @@ namespace sm100 {
 constexpr int kThreads = 384;
 constexpr int kBM = 128;                      // rows per query tile (two tiles per CTA)
 constexpr int kBN = 128;                      // keys per KV tile
-constexpr int kD = 128;
 constexpr int kHalfBytes = 128 * 128;         // 128 lines of 128 B: one 64-column half of a tile
 constexpr int kTileBytes = 2 * kHalfBytes;    // 32 KB
 constexpr int kRingBytes = 4 * kTileBytes;    // K/V ring: 4 stages of a tile, or (PAIR) 8 stages of half a tile
@@ -65,6 +64,11 @@ constexpr float kRescaleThreshold = 8.f;      // log2 units
 #define MOJO_ATTN_EMU_PAIRS 2
 #endif
 constexpr int kEmuPairs = MOJO_ATTN_EMU_PAIRS;  // of every 8 pairs of exponentials, this many run on the FMA pipe
+#ifndef MOJO_ATTN_EMU_PAIRS_D64
+#define MOJO_ATTN_EMU_PAIRS_D64 3
+#endif
+// head_dim 64 has half the tensor work per exponential: the MUFU is further ahead of the tensor pipe as the limiter
+constexpr int kEmuPairsD64 = MOJO_ATTN_EMU_PAIRS_D64;
 #ifndef MOJO_ATTN_LAZY_REF
 #define MOJO_ATTN_LAZY_REF 1
 #endif
@@ -853,7 +857,7 @@ int launch_attn_sm100(const AttnSm100Args& a, cudaStream_t stream) {
   cfg.numAttrs = pair ? 1 : 0;
 #define LAUNCH_SM100_P(TT, PP, RR, WW, PAIR_, DD)                                                             \
   do {                                                                                                        \
-    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, kEmuPairs, PAIR_, WW, DD>;                                  \
+    auto kern = attn_fwd_sm100_kernel<TT, PP, RR, (DD == 64 ? kEmuPairsD64 : kEmuPairs), PAIR_, WW, DD>;                                  \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));   \
     MOJO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, q_map, k_map, v_map, p));                                      \
   } while (0)
