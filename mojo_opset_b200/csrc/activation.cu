@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256, 4) act_kernel(const T* __restrict__ gate,
                                                   int64_t u_rs, int64_t o_rs, float limit) {
   constexpr int N = Vec16<T>::N;
   const int64_t vecs = cols / N;
+  pdl_wait();
+  pdl_trigger();
   for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
     const T* g = gate + row * g_rs;
     const T* u = GATED ? up + row * u_rs : nullptr;
@@ -172,10 +174,11 @@ static int act_entry(const void* gate, const void* up, void* out, int64_t rows, 
   return dispatch_dtype(dtype, [&](auto tag) {
     using T = decltype(tag);
     if (vec_ok) {
-      if (gated && limit > 0.f) act_kernel<T, true, true><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
-      else if (gated) act_kernel<T, true, false><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
-      else if (gelu) act_kernel<T, false, false, true><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
-      else act_kernel<T, false, false><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);
+      const int64_t zero = 0;
+      if (gated && limit > 0.f) launch_pdl(act_kernel<T, true, true>, grid, dim3(256), 0, s, (const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
+      else if (gated) launch_pdl(act_kernel<T, true, false>, grid, dim3(256), 0, s, (const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
+      else if (gelu) launch_pdl(act_kernel<T, false, false, true>, grid, dim3(256), 0, s, (const T*)gate, (const T*)nullptr, (T*)out, rows, cols, g_rs, zero, o_rs, 0.f);
+      else launch_pdl(act_kernel<T, false, false>, grid, dim3(256), 0, s, (const T*)gate, (const T*)nullptr, (T*)out, rows, cols, g_rs, zero, o_rs, 0.f);
     } else {
       if (gated) act_scalar_kernel<T, true><<<grid, 256, 0, s>>>((const T*)gate, (const T*)up, (T*)out, rows, cols, g_rs, u_rs, o_rs, limit);
       else if (gelu) act_scalar_kernel<T, false, true><<<grid, 256, 0, s>>>((const T*)gate, nullptr, (T*)out, rows, cols, g_rs, 0, o_rs, 0.f);

@@ -28,6 +28,11 @@ int* error_word() {
   return g_error_word[dev];
 }
 
+bool pdl_enabled() {
+  const char* v = getenv("MOJO_B200_PDL");
+  return !(v && v[0] == '0');
+}
+
 }  // namespace mojo
 
 extern "C" {

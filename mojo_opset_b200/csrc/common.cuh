@@ -8,6 +8,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/mojo_b200.h"
 
@@ -93,6 +95,34 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// The path is a chain of short dependent kernels (norm -> RoPE -> store -> decode -> SwiGLU / o_proj): with a plain
+// launch every link pays the full drain + launch latency of its predecessor.  Kernels launched through launch_pdl()
+// carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become resident while the previous kernel's
+// last wave drains and run their prologue (barrier init, descriptor / weight prefetch); pdl_wait() blocks until the
+// previous kernel has COMPLETED and its writes are visible, so every such kernel calls it before it touches any
+// memory another kernel may have produced (completion is transitive along the chain: each link waits itself).
+// pdl_trigger() lets the NEXT kernel's CTAs be scheduled; it sits after the wait so at most one successor is staged.
+// MOJO_B200_PDL=0 turns the attribute off (plain stream order; the device-side calls are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // api.cu
+
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -34,13 +34,18 @@ namespace gar {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;
 constexpr int kStages = 5;
+#ifndef MOJO_GAR_STAGES_PAIR
+#define MOJO_GAR_STAGES_PAIR 7
+#endif
+constexpr int kStagesPair = MOJO_GAR_STAGES_PAIR;                // CTA pairs stage only half of B: 24 KB per stage
 constexpr int kSlabBytes = kBM * kBK * 2;     // 16 KB: one operand slab of one stage
 constexpr int kStageBytes = 2 * kSlabBytes;   // A + B
 constexpr int kImageBytes = kBM * kBN * 2;    // 32 KB: one output tile, 16-bit elements
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kMaxWorld = 8;
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kImageBytes + 256;
+constexpr size_t kSmemBytes = 1024 + (size_t)kStagesPair * (kSlabBytes + kSlabBytes / 2) + kImageBytes + 256;
+static_assert((size_t)kStagesPair * (kSlabBytes + kSlabBytes / 2) >= (size_t)kStages * kStageBytes, "ring sized by the pair mode");
 // a waiting rank gives up (trap: launch failure rather than a hung GPU) only after MOJO_B200_GAR_TIMEOUT_S seconds (default
 // 600, 0 = wait for ever like NCCL): ranks of an eager serving loop may skew by seconds (GC pause, first-call module load)
 constexpr unsigned long long kDefaultWaitTimeoutNs = 600ull * 1000000000ull;
@@ -58,10 +63,23 @@ struct Params {
   int tiles_cap;    // result images per parity = max tiles
   uint8_t* ws[kMaxWorld];  // workspace base of every rank as mapped HERE (ws[rank] is local memory)
   size_t off_partial, off_result, off_flag_partial, off_flag_result;
+  int n_pair_tiles;  // PAIR: work items of a 2-CTA cluster = (256-row block, 128-column block)
   int one_shot, one_cap;  // one-shot mode: slots [parity][tile < one_cap][src], flags alike
   size_t off_one, off_flag_one;
   unsigned long long timeout_ns;  // 0 = never give up
+  int prefetch;       // B slabs pulled into L2 ahead of the ring (MOJO_B200_GAR_PREFETCH, k-blocks; 0 = off)
+  long long* trace;   // developer timeline (MOJO_GAR_TRACE builds only, tools/gar_trace.py)
 };
+
+#ifdef MOJO_GAR_TRACE
+// role 0 producer / 1 MMA or relay / 2 epilogue warp 2; CTAs 0 and 1; 96 slots each
+#define GTRACE(role, j)                                                                                  \
+  do {                                                                                                   \
+    if (p.trace && blockIdx.x < 2 && (j) < 96 && (j) >= 0) p.trace[((role) + 3 * blockIdx.x) * 96 + (j)] = clock64(); \
+  } while (0)
+#else
+#define GTRACE(role, j) do {} while (0)
+#endif
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -111,6 +129,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
 // shared -> global (local or peer) bulk copy, tracked by the bulk async-group of the issuing thread
 __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
@@ -179,63 +203,126 @@ template <typename T> __device__ __forceinline__ void acc2(float (&a)[8], const 
   }
 }
 
-template <typename T>
+// PAIR = true: the same kernel on 2-CTA clusters with cta_group::2 MMAs (M = 256 = the two CTAs' 128-row blocks of x
+// against ONE 128-column block of W, of which each CTA stages 64 rows): per k-block a CTA takes 16 KB of A + 8 KB of B
+// out of L2 instead of 16 + 16 - at 128 x 128 single-CTA tiles the GEMM sat on the chip's L2 -> SM throughput cap
+// (~6300 B/clk).  The leader CTA issues the MMAs; the peer relays "my slabs landed" to the leader's ring barriers,
+// commits multicast to both CTAs; each CTA runs the epilogue of its own 128 rows (its own TMEM lanes).
+template <typename T, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
                       const Params p) {
+  constexpr int kStg = PAIR ? kStagesPair : kStages;
+  constexpr int kBBytes = PAIR ? kSlabBytes / 2 : kSlabBytes;
+  constexpr int kStgBytes = kSlabBytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
-  uint8_t* image = smem + kStages * kStageBytes;
+  uint8_t* image = smem + kStg * kStgBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(image + kImageBytes);
-  uint64_t* full = bars;                    // [kStages]
-  uint64_t* empty = bars + kStages;         // [kStages]
-  uint64_t* acc_full = empty + kStages;     // [2]
+  uint64_t* full = bars;                    // [kStg]
+  uint64_t* empty = bars + kStg;            // [kStg]
+  uint64_t* acc_full = empty + kStg;        // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint64_t* aux_bar = acc_empty + 2;        // bulk loads of the reduce / copy phases
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
   uint32_t* epoch_slot = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  if (threadIdx.x == 64) GTRACE(2, 0);
+  // GEMM work items of this CTA (PAIR: of its cluster): w = w0, w0 + wstep, ... < n_work
+  const int n_work = PAIR ? p.n_pair_tiles : p.n_tiles;
+  const int w0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int k_blocks = (int)((p.k + kBK - 1) / kBK);
+  // PAIR: this CTA stages rows [128 (2 tm + rank), +128) of x and rows [128 tn + 64 rank, +64) of W
+  const int b_row_off = PAIR ? (int)crank * (kBN / 2) : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 1);
+    // descriptor fetches first: a TMA instruction whose descriptor is not cached yet holds its thread for the whole
+    // fetch (timeline: ~2000 cycles for the first load issued right behind the prefetch); the TMEM allocation, the CTA
+    // barrier and the cluster handshake below cover it
+    tma_prefetch_desc(&b_map);
+    tma_prefetch_desc(&a_map);
+    for (int s = 0; s < kStg; ++s) {
+      mbar_init(&full[s], (PAIR && crank == 0) ? 2 : 1);  // leader: own TMA + the peer's relay
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
     mbar_init(aux_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, 256); else tmem_alloc(tmem_slot, 256);
+  }
   // The call's epoch lives in DEVICE memory (the workspace header), so a CUDA graph can replay the launch: every
   // CTA reads the counter at its start, the last CTA to finish publishes the new value.  A CTA can only finish
   // after every CTA of the grid has started (the finished-CTA count reaches gridDim.x), so all of them read the
   // same value.  1 .. 0xFFFFFFFE, never 0 (the flags' initial value), parity alternates across the wrap.
-  if (threadIdx.x == 64)
-    *epoch_slot = p.world > 1 ? *reinterpret_cast<volatile uint32_t*>(p.ws[p.rank]) % 0xFFFFFFFEu + 1u : 1u;
+  // (read after pdl_wait() by the first epilogue thread: the previous call's last CTA publishes the counter at its end)
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  const int k_blocks = (int)((p.k + kBK - 1) / kBK);
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      tma_prefetch_desc(&a_map);
-      tma_prefetch_desc(&b_map);
+      // The weights do not depend on the previous kernel (PDL): the B slabs of the first ring pass are requested (and
+      // the next p.prefetch slabs of that column pulled into L2; the loop keeps that distance) BEFORE pdl_wait(), i.e.
+      // while the previous kernel - the decode that just streamed gigabytes through L2 - drains; x (A) follows after it.
+      int pre = 0;
+      if (w0 < n_work) {
+        const int tn0 = w0 % p.tiles_n;
+        pre = k_blocks < kStg ? k_blocks : kStg;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_expect_tx(&full[kb], kStgBytes);
+          tma_load_2d(ring + kb * kStgBytes + kSlabBytes, &b_map, &full[kb], kb * kBK, tn0 * kBN + b_row_off);
+        }
+        const int pf_end = k_blocks < pre + p.prefetch ? k_blocks : pre + p.prefetch;
+        for (int kb = pre; kb < pf_end; ++kb) tma_prefetch_l2_2d(&b_map, kb * kBK, tn0 * kBN + b_row_off);
+      }
+      GTRACE(0, 0);
+      pdl_wait();
       uint32_t c = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      for (int w = w0; w < n_work; w += wstep) {
+        const int tmw = w / p.tiles_n, tn = w - tmw * p.tiles_n;
+        const int a_row = (PAIR ? 2 * tmw + (int)crank : tmw) * kBM;
         for (int kb = 0; kb < k_blocks; ++kb, ++c) {
-          const uint32_t s = c % kStages;
-          mbar_wait_bounded(&empty[s], ((c / kStages) & 1u) ^ 1u);
-          mbar_expect_tx(&full[s], kStageBytes);
-          tma_load_2d(ring + s * kStageBytes, &a_map, &full[s], kb * kBK, tm * kBM);
-          tma_load_2d(ring + s * kStageBytes + kSlabBytes, &b_map, &full[s], kb * kBK, tn * kBN);
+          const uint32_t s = c % kStg;
+          if ((int)c < pre) {  // B of this stage is already on its way
+            tma_load_2d(ring + s * kStgBytes, &a_map, &full[s], kb * kBK, a_row);
+            continue;
+          }
+          mbar_wait_bounded(&empty[s], ((c / kStg) & 1u) ^ 1u);
+          GTRACE(0, (int)c + 1);
+#ifdef MOJO_GAR_DBG_NOTMA  // developer experiment: no operand traffic after the first ring pass (results garbage)
+          mbar_arrive(&full[s]);
+          continue;
+#endif
+          mbar_expect_tx(&full[s], kStgBytes);
+          tma_load_2d(ring + s * kStgBytes, &a_map, &full[s], kb * kBK, a_row);
+          tma_load_2d(ring + s * kStgBytes + kSlabBytes, &b_map, &full[s], kb * kBK, tn * kBN + b_row_off);
+          if (kb + p.prefetch < k_blocks) tma_prefetch_l2_2d(&b_map, (kb + p.prefetch) * kBK, tn * kBN + b_row_off);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && PAIR && crank != 0) {
+    // ------------------------------------------------------------------------------------ peer relay: "my slabs landed"
+    if (lane == 0) {
+      const uint32_t lead_full = mapa_u32(smem_u32(full), 0);
+      uint32_t c = 0;
+      for (int w = w0; w < n_work; w += wstep) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++c) {
+          const uint32_t s = c % kStg;
+          mbar_wait_bounded(&full[s], (c / kStg) & 1u);
+          GTRACE(1, (int)c + 1);
+          mbar_arrive_cluster(lead_full + s * 8u);
         }
       }
     }
@@ -243,26 +330,30 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------ MMA issuer (whole warp)
     constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-    constexpr uint32_t idesc = umma_idesc_f16(kFmt, kBM, kBN, 0, 0);
-    const uint32_t ring_a = smem_u32(ring);
+    constexpr uint32_t idesc = umma_idesc_f16(kFmt, PAIR ? 2 * kBM : kBM, kBN, 0, 0);
+    const uint64_t desc_a0 = umma_desc_sw128(smem_u32(ring), 16, 1024);  // ring offsets stay inside the 14-bit address field
     uint32_t c = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (int w = w0; w < n_work; w += wstep, ++it) {
       const int a = it & 1;
       mbar_wait_bounded(&acc_empty[a], (((uint32_t)it >> 1) & 1u) ^ 1u);
       tc_fence_after();
       for (int kb = 0; kb < k_blocks; ++kb, ++c) {
-        const uint32_t s = c % kStages;
-        mbar_wait_bounded(&full[s], (c / kStages) & 1u);
+        const uint32_t s = c % kStg;
+        mbar_wait_bounded(&full[s], (c / kStg) & 1u);  // PAIR: in both CTAs (the relay arrives on the same barrier)
+        if (lane == 0) GTRACE(1, (int)c + 1);
         tc_fence_after();
-        const uint32_t sa = ring_a + s * kStageBytes, sb = sa + kSlabBytes;
-#pragma unroll
-        for (int ks = 0; ks < kBK / 16; ++ks)
-          umma_ss(tmem + a * kBN, umma_desc_sw128(sa + ks * 32, 16, 1024), umma_desc_sw128(sb + ks * 32, 16, 1024), idesc,
-                  (kb | ks) != 0);
-        umma_commit(&empty[s]);
+        // the four K-steps of the stage in ONE asm block (one elect, descriptors derived by 64-bit adds): issued one by
+        // one, the descriptor / elect / R2UR chains of the single issuing warp took ~97 cycles per MMA against 65 of
+        // tensor work (timeline with the operand traffic switched off: the same 388 cycles per k-block)
+        const uint64_t da = desc_a0 + (uint64_t)((s * (uint32_t)kStgBytes) >> 4);
+        const uint64_t db = da + (uint64_t)(kSlabBytes >> 4);
+        static_assert(kBK == 64, "x4 issue = four K-steps of 16 inside one 128-byte swizzle row");
+        if (PAIR) umma_ss_x4_pair(tmem + a * kBN, da, db, idesc, kb != 0);
+        else umma_ss_x4(tmem + a * kBN, da, db, idesc, kb != 0);
+        if (PAIR) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);
       }
-      umma_commit(&acc_full[a]);
+      if (PAIR) umma_commit_pair(&acc_full[a]); else umma_commit(&acc_full[a]);
     }
     __syncwarp();
   } else {
@@ -270,6 +361,11 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;          // row of the tile
     const int tid = threadIdx.x - 64;       // 0..127
+    pdl_wait();
+    pdl_trigger();
+    if (tid == 0)
+      *epoch_slot = p.world > 1 ? *reinterpret_cast<volatile uint32_t*>(p.ws[p.rank]) % 0xFFFFFFFEu + 1u : 1u;
+    epi_barrier();
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(epoch_slot);
     const uint32_t par = epoch & 1u;
     T* out = reinterpret_cast<T*>(p.out);
@@ -294,12 +390,23 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
       }
     };
 
+    const uint32_t lead_acc_empty = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
     int it = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (int w = w0; w < n_work; w += wstep, ++it) {
       const int a = it & 1;
-      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      const int tmw = w / p.tiles_n, tn = w - tmw * p.tiles_n;
+      const int tm = PAIR ? 2 * tmw + (int)crank : tmw;
+      const int t = tm * p.tiles_n + tn;            // the 128 x 128 output tile this CTA holds
+      const bool tile_valid = tm < p.tiles_m;       // PAIR: the peer's row block may lie past m (an odd number of them)
       mbar_wait_bounded(&acc_full[a], ((uint32_t)it >> 1) & 1u);
+      if (tid == 0) GTRACE(2, 1 + 2 * it);
       tc_fence_after();
+      if (!tile_valid) {  // nothing to keep: hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_acc_empty + (uint32_t)a * 8u);
+        continue;
+      }
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         uint32_t r[32];
@@ -326,11 +433,14 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[a]);  // the MMA warp may start the tile after next
+      if (lane == 0) {  // the MMA warp may start the tile after next
+        if (PAIR) mbar_arrive_cluster(lead_acc_empty + (uint32_t)a * 8u); else mbar_arrive(&acc_empty[a]);
+      }
       if (p.world == 1) {
         epi_barrier();
         image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(image + off); }, tm, tn);
         epi_barrier();
+        if (tid == 0) GTRACE(2, 2 + 2 * it);
       } else {
         fence_async_smem();
         epi_barrier();
@@ -472,9 +582,10 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    if (PAIR) tmem_dealloc_pair(tmem, 256); else tmem_dealloc(tmem, 256);
   }
   if (p.world > 1 && threadIdx.x == 0) {
     uint32_t* hdr = reinterpret_cast<uint32_t*>(p.ws[p.rank]);
@@ -487,7 +598,8 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
   }
 }
 
-static int build_2d_map(const void* base, int dtype, int64_t rows, int64_t cols, int64_t row_stride, CUtensorMap* out) {
+static int build_2d_map(const void* base, int dtype, int64_t rows, int64_t cols, int64_t row_stride, int box_rows,
+                        CUtensorMap* out) {
   TensorMapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
@@ -495,8 +607,43 @@ static int build_2d_map(const void* base, int dtype, int64_t rows, int64_t cols,
   key.dtype = dtype;
   key.swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B;
   key.dims[0] = (uint64_t)cols;  key.box[0] = kBK;
-  key.dims[1] = (uint64_t)rows;  key.strides[0] = (uint64_t)row_stride * 2;  key.box[1] = kBM;
+  key.dims[1] = (uint64_t)rows;  key.strides[0] = (uint64_t)row_stride * 2;  key.box[1] = (uint32_t)box_rows;
   return get_tensor_map(key, out);
+}
+
+static bool env_flag(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) != 0 : fallback != 0;
+}
+
+// Can this device / context co-schedule 2-CTA clusters of this kernel (one CTA per SM by shared memory)?  Asked once
+// per device; on a partitioned GPU the answer can be "none" and the launcher stays with single CTAs.
+static bool pair_clusters_fit() {
+  static int cached[64];  // 0 = not asked, 1 = yes, 2 = no
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (cached[dev] == 0) {
+    auto kern = gemm_allreduce_kernel<__nv_bfloat16, true>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // clear: the question failed, the answer is "no"
+      n = 0;
+    }
+    cached[dev] = n > 0 ? 1 : 2;
+  }
+  return cached[dev] == 1;
 }
 
 }  // namespace gar
@@ -574,6 +721,11 @@ extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const
   p.n_tiles = (int)tiles;
   p.world = world; p.rank = rank;
   p.timeout_ns = kDefaultWaitTimeoutNs;
+  p.prefetch = 0;
+  if (const char* pf = getenv("MOJO_B200_GAR_PREFETCH")) p.prefetch = atoi(pf);
+#ifdef MOJO_GAR_TRACE
+  if (const char* tp = getenv("MOJO_B200_GAR_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(tp, nullptr, 0));
+#endif
   if (const char* t = getenv("MOJO_B200_GAR_TIMEOUT_S")) p.timeout_ns = (unsigned long long)(atof(t) * 1e9);
   if (world > 1) {
     MOJO_REQUIRE(peer_workspaces, MOJO_B200_EINVAL, "gemm_allreduce: peer workspace table is null");
@@ -598,27 +750,48 @@ extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const
     }
   }
 
+  // CTA pairs (cta_group::2, 256 x 128 work items) once there are at least two 128-row blocks to pair up
+  const bool pair = p.tiles_m >= 2 && env_flag("MOJO_B200_GAR_PAIR", 1) && pair_clusters_fit();
+  p.n_pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
+
   CUtensorMap a_map, b_map;
-  int rc = build_2d_map(x, dtype, m, k, x_row_stride, &a_map);
+  int rc = build_2d_map(x, dtype, m, k, x_row_stride, kBM, &a_map);
   if (rc != 0) return rc;
-  rc = build_2d_map(weight, dtype, n, k, w_row_stride, &b_map);
+  rc = build_2d_map(weight, dtype, n, k, w_row_stride, pair ? kBN / 2 : kBN, &b_map);
   if (rc != 0) return rc;
 
   int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+  if (pair) grid = 2 * (p.n_pair_tiles < kNumSMs / 2 ? p.n_pair_tiles : kNumSMs / 2);
   // several virtual ranks sharing ONE GPU (comm.LocalRanks) must all be resident at once: cap each rank's CTAs
   if (const char* cap = getenv("MOJO_B200_GAR_MAX_CTAS")) {
-    const int c = atoi(cap);
+    int c = atoi(cap);
+    if (pair) c &= ~1;
     if (c > 0 && c < grid) grid = c;
   }
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pair ? 2 : 1;
+#define GAR_LAUNCH(TT, PP)                                                                                     \
+  do {                                                                                                         \
+    auto kern = gemm_allreduce_kernel<TT, PP>;                                                                 \
+    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));    \
+    MOJO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a_map, b_map, p));                                             \
+  } while (0)
   if (dtype == MOJO_B200_BF16) {
-    auto kern = gemm_allreduce_kernel<__nv_bfloat16>;
-    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, s>>>(a_map, b_map, p);
+    if (pair) GAR_LAUNCH(__nv_bfloat16, true); else GAR_LAUNCH(__nv_bfloat16, false);
   } else {
-    auto kern = gemm_allreduce_kernel<__half>;
-    MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, s>>>(a_map, b_map, p);
+    if (pair) GAR_LAUNCH(__half, true); else GAR_LAUNCH(__half, false);
   }
+#undef GAR_LAUNCH
   return check_launch("gemm_allreduce_kernel");
 }

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(kNrsThreads, 5) norm_rope_store_kernel(const N
   constexpr bool ROUND_T = std::is_same<T, C>::value;  // intermediates of a same-dtype RoPE are rounded to T
   const int64_t tok = blockIdx.x;
   const int sl = threadIdx.x % LPH, hs = threadIdx.x / LPH;
+  pdl_wait();
+  pdl_trigger();
 
   // ---- this lane's role inside a head and its cos / sin / norm-weight slices
   const int nope = D - a.rope_dim, half = a.rope_dim / 2;
@@ -314,8 +316,8 @@ extern "C" int mojo_b200_norm_rope_store_kv(
   const bool cos_f32 = cos_dtype == MOJO_B200_F32;
 #define NRS_LAUNCH(TT, CC, LL)                                                                \
   do {                                                                                        \
-    if (norm) norm_rope_store_kernel<TT, CC, LL, true><<<grid, kNrsThreads, 0, s>>>(a);       \
-    else norm_rope_store_kernel<TT, CC, LL, false><<<grid, kNrsThreads, 0, s>>>(a);           \
+    if (norm) launch_pdl(norm_rope_store_kernel<TT, CC, LL, true>, dim3(grid), dim3(kNrsThreads), 0, s, a);  \
+    else launch_pdl(norm_rope_store_kernel<TT, CC, LL, false>, dim3(grid), dim3(kNrsThreads), 0, s, a);      \
   } while (0)
 #define NRS_DIM(TT, CC)                                        \
   do {                                                         \

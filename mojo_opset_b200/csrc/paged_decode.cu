@@ -131,6 +131,20 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // prologue that touches no other kernel's data (PDL: runs while the previous kernel drains)
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kConsumerWarps && lane == 0) {
+    tma_prefetch_desc(&k_map);
+    tma_prefetch_desc(&v_map);
+  }
+  pdl_wait();
+  pdl_trigger();
   const int seq_len = p.seq_lens[b];
   const int rows_valid = min(16, p.group - ht * 16);  // query heads in this tile
   // the reference raises ValueError for a row with keys but no first block (attention.py:186-187): flag it
@@ -158,13 +172,6 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
     return;
   }
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
-    }
-    mbar_fence_init();
-  }
   __syncthreads();
 
   const int log2_bs = p.log2_bs;
@@ -173,10 +180,6 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
 
   if (warp == kConsumerWarps) {
     // ------------------------------------------------------------------ producer warp
-    if (lane == 0) {
-      tma_prefetch_desc(&k_map);
-      tma_prefetch_desc(&v_map);
-    }
     const int32_t* table = p.tables + (int64_t)b * p.table_stride;
     const uint32_t box_bytes = (uint32_t)box_rows * D * 2;
     for (int it = 0; it < n_tiles; ++it) {
@@ -421,6 +424,8 @@ __global__ void __launch_bounds__(256) paged_decode_simt_kernel(const DecodePara
   const int ht = blockIdx.y - kvh * p.head_tiles;
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   const int seq_len = p.seq_lens[b];
   const int rows_valid = min(GH, p.group - ht * GH);
   if (p.err && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && seq_len > 0 && p.max_blocks > 0 &&
@@ -525,26 +530,68 @@ __global__ void __launch_bounds__(256) paged_decode_simt_kernel(const DecodePara
 // ======================================================================================================
 // second pass: fold the per-split partials
 // ======================================================================================================
+// One CTA (4 warps) per (query head, sequence).  Every warp finds the global maximum and the normaliser from the
+// (m, l) pairs (a lane per split), then accumulates the partial rows of the splits s = warp, warp + 4, ... - four
+// rows requested per trip, so a 37-split fold (batch 1, 32k context) is ~3 load round trips instead of 37 - and the
+// four warps' sums meet in shared memory.
 template <typename T>
 __global__ void __launch_bounds__(128) paged_decode_reduce_kernel(const float* __restrict__ part_o,
                                                                   const float2* __restrict__ part_ml,
                                                                   T* __restrict__ out, int num_q_heads, int head_dim,
                                                                   int num_splits, int64_t o_sb, int64_t o_sh) {
+  constexpr int kWarps = 4, kMaxDpl = 8;  // head_dim <= 256
+  __shared__ float s_acc[kWarps][256];
   const int hq = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t base = ((int64_t)b * num_q_heads + hq) * num_splits;
+  const int dpl = (head_dim + 31) >> 5;
+  pdl_wait();
+  pdl_trigger();
   float m = -INFINITY;
-  for (int s = 0; s < num_splits; ++s) m = fmaxf(m, part_ml[base + s].x);
-  for (int d = threadIdx.x; d < head_dim; d += blockDim.x) {
-    float l = 0.f, acc = 0.f;
-    for (int s = 0; s < num_splits; ++s) {
-      const float2 ml = part_ml[base + s];
-      if (ml.x != -INFINITY) {
-        const float f = exp2f(ml.x - m);
+  for (int s0 = 0; s0 < num_splits; s0 += 32)
+    if (s0 + lane < num_splits) m = fmaxf(m, part_ml[base + s0 + lane].x);
+  m = warp_max(m);
+  float l = 0.f;
+  float acc[kMaxDpl];
+#pragma unroll
+  for (int j = 0; j < kMaxDpl; ++j) acc[j] = 0.f;
+  for (int s0 = 0; s0 < num_splits; s0 += 32) {
+    float f = 0.f;
+    if (s0 + lane < num_splits) {
+      const float2 ml = part_ml[base + s0 + lane];
+      if (ml.x != -INFINITY) {  // an empty split contributes nothing
+        f = exp2f(ml.x - m);
         l += f * ml.y;
-        acc += f * part_o[(base + s) * head_dim + d];
       }
     }
-    out[b * o_sb + hq * o_sh + d] = DType<T>::from_f(l > 0.f ? acc / l : 0.f);
+    const int n = min(32, num_splits - s0);
+    for (int i = warp; i < n; i += 4 * kWarps) {  // four of this warp's splits per trip
+      float v[4][kMaxDpl], fs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int si = i + u * kWarps;
+        fs[u] = __shfl_sync(0xffffffffu, f, si & 31);
+        const float* row = part_o + (base + s0 + si) * head_dim;
+#pragma unroll
+        for (int j = 0; j < kMaxDpl; ++j) v[u][j] = (si < n && j < dpl && lane + 32 * j < head_dim) ? row[lane + 32 * j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i + u * kWarps < n && fs[u] != 0.f) {  // (an empty split's row is uninitialised memory)
+#pragma unroll
+          for (int j = 0; j < kMaxDpl; ++j) acc[j] = fmaf(fs[u], v[u][j], acc[j]);
+        }
+      }
+    }
+  }
+  l = warp_sum(l);
+#pragma unroll
+  for (int j = 0; j < kMaxDpl; ++j)
+    if (j < dpl && lane + 32 * j < head_dim) s_acc[warp][lane + 32 * j] = acc[j];
+  __syncthreads();
+  for (int d = threadIdx.x; d < head_dim; d += blockDim.x) {
+    const float a = (s_acc[0][d] + s_acc[1][d]) + (s_acc[2][d] + s_acc[3][d]);
+    out[b * o_sb + hq * o_sh + d] = DType<T>::from_f(l > 0.f ? a / l : 0.f);
   }
 }
 
@@ -714,7 +761,7 @@ static int paged_decode_impl(
   do {                                                                                                   \
     auto kern = paged_decode_mma_kernel<TT, DD, SH>;                                                     \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    kern<<<grid, kDecodeThreads, smem, s>>>(k_map, v_map, p);                                            \
+    MOJO_CUDA_OK(launch_pdl(kern, grid, dim3(kDecodeThreads), smem, s, k_map, v_map, p));                \
   } while (0)
     if (dtype == MOJO_B200_BF16) {
       if (head_dim == 128) { if (split_halves) LAUNCH_FAST(__nv_bfloat16, 128, true); else LAUNCH_FAST(__nv_bfloat16, 128, false); }
@@ -732,7 +779,7 @@ static int paged_decode_impl(
   do {                                                                                                  \
     auto kern = paged_decode_simt_kernel<TT, GG, DP>;                                                   \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<grid, 256, smem, s>>>(p);                                                                    \
+    MOJO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, s, p));                                        \
   } while (0)
 #define SIMT_BY_D(TT, GG)                              \
   do {                                                 \
@@ -755,8 +802,9 @@ static int paged_decode_impl(
     dim3 rgrid((unsigned)num_q_heads, (unsigned)batch);
     int rc = dispatch_dtype(dtype, [&](auto tag) {
       using TT = decltype(tag);
-      paged_decode_reduce_kernel<TT><<<rgrid, 128, 0, s>>>(p.part_o, p.part_ml, (TT*)out, num_q_heads, head_dim,
-                                                          num_splits, o_stride_b, o_stride_h);
+      MOJO_CUDA_OK(launch_pdl(paged_decode_reduce_kernel<TT>, rgrid, dim3(128), 0, s, (const float*)p.part_o,
+                              (const float2*)p.part_ml, (TT*)out, num_q_heads, head_dim, num_splits, o_stride_b,
+                              o_stride_h));
       return 0;
     });
     if (rc) return rc;

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kerne
     float eps) {
   constexpr int N = VEC;
   constexpr int ROWS_PER_CTA = (TPR >= kNormCta ? 1 : kNormCta / TPR);
+  pdl_wait();
+  pdl_trigger();
   const int lane_in_row = threadIdx.x % TPR;
   const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + threadIdx.x / TPR;
   const bool active = row < rows;
@@ -142,9 +144,9 @@ static int launch_rmsnorm(const void* x, const void* res, const void* w, void* y
   do {                                                                                                        \
     constexpr int RPC = (TPR >= kNormCta ? 1 : kNormCta / TPR);                                               \
     const int64_t ctas = (rows + RPC - 1) / RPC;                                                              \
-    rmsnorm_kernel<T, VEC, TPR, HAS_RES><<<(unsigned)ctas, (TPR > kNormCta ? TPR : kNormCta), 0, s>>>(        \
-        (const T*)x, (const T*)res, (const T*)w, (T*)y, (T*)sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs, \
-        eps);                                                                                                 \
+    launch_pdl(rmsnorm_kernel<T, VEC, TPR, HAS_RES>, dim3((unsigned)ctas), dim3(TPR > kNormCta ? TPR : kNormCta), 0, s, \
+               (const T*)x, (const T*)res, (const T*)w, (T*)y, (T*)sum_out, rows, hidden, x_rs, res_rs, y_rs, sum_rs,  \
+               eps);                                                                                          \
   } while (0)
   // the narrowest group that keeps the row register-resident with FOUR 16-byte loads in flight per thread
   // (4 packs of x, or 2 of x + 2 of the residual): measured best on B200 - wider groups pay for the CTA-level

@@ -97,6 +97,8 @@ template <typename T, typename C, int VEC, bool ROUND_T, int SLICES>
 __global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs a) {
   constexpr int HSLOTS = 256 / SLICES;
   const int sl = threadIdx.x % SLICES, hs = threadIdx.x / SLICES;
+  pdl_wait();
+  pdl_trigger();
   const int nope = a.head_dim - a.rope_dim, half = a.rope_dim / 2;
   const int off = sl * VEC;  // this thread's output slice inside a head
   const bool rotary = off >= nope;
@@ -223,9 +225,9 @@ static bool launch_rope_fast(const RopeArgs& a, int64_t tokens, cudaStream_t s) 
   const int64_t cap = (int64_t)kNumSMs * 4 * 3;
   const unsigned grid = (unsigned)(tokens < cap ? tokens : cap);
   switch (a.head_dim / VEC) {
-    case 8: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 8><<<grid, 256, 0, s>>>(a); return true;
-    case 16: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 16><<<grid, 256, 0, s>>>(a); return true;
-    case 32: apply_rope_slice_kernel<T, C, VEC, ROUND_T, 32><<<grid, 256, 0, s>>>(a); return true;
+    case 8: launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, 8>, dim3(grid), dim3(256), 0, s, a); return true;
+    case 16: launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, 16>, dim3(grid), dim3(256), 0, s, a); return true;
+    case 32: launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, 32>, dim3(grid), dim3(256), 0, s, a); return true;
     default: return false;
   }
 }

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256) store_chunks_kernel(
     const char* __restrict__ ks, const char* __restrict__ vs, char* __restrict__ kc, char* __restrict__ vc,
     const int32_t* __restrict__ plan, int64_t num_tokens, int num_kv_heads, int row_bytes, int64_t num_blocks,
     int block_size, StoreStrides st) {
+  pdl_wait();
+  pdl_trigger();
   const int4 row = reinterpret_cast<const int4*>(plan)[blockIdx.x];
   const int src = row.x, blk = row.y, off = row.z, len = row.w;
   if (len <= 0 || src < 0 || (int64_t)src + len > num_tokens) return;
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(128) store_table_kernel(
     const int32_t* __restrict__ ctx_lens, int num_seqs, int64_t num_tokens, int num_kv_heads, int row_bytes,
     int64_t num_blocks, int block_size, StoreStrides st) {
   const int64_t tok = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
   // The token's rows are requested BEFORE its page slot is looked up: the lookup is a chain of four to six dependent
   // loads (binary search over cu_q_lens, context length, block table) and a CTA moves only 4 KB, so with the rows
   // issued after it the CTA's life was almost all lookup latency (0.70 of the HBM peak at T = 8192).
@@ -191,9 +195,9 @@ extern "C" int mojo_b200_store_paged_kv_chunks(
   dim3 grid((unsigned)num_chunks, (unsigned)ysplit);
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(VB)                                                                                              \
-  store_chunks_kernel<VB><<<grid, 256, 0, s>>>((const char*)key_states, (const char*)value_states,               \
-                                               (char*)key_cache, (char*)value_cache, chunk_metadata, num_tokens, \
-                                               num_kv_heads, row_bytes, num_blocks, block_size, st)
+  launch_pdl(store_chunks_kernel<VB>, grid, dim3(256), 0, s, (const char*)key_states, (const char*)value_states, \
+             (char*)key_cache, (char*)value_cache, chunk_metadata, num_tokens, num_kv_heads, row_bytes, num_blocks, \
+             block_size, st)
   switch (vb) {
     case 16: LAUNCH(16); break;
     case 8: LAUNCH(8); break;
@@ -226,10 +230,10 @@ extern "C" int mojo_b200_store_paged_kv_table(
   const int vb = pick_vec_bytes(row_bytes, st, key_states, value_states, key_cache, value_cache);
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(VB)                                                                                               \
-  store_table_kernel<VB><<<(unsigned)num_tokens, 128, 0, s>>>(                                                    \
-      (const char*)key_states, (const char*)value_states, (char*)key_cache, (char*)value_cache, block_table,      \
-      table_stride, max_blocks_per_seq, cu_q_lens, context_kv_lens, num_seqs, num_tokens, num_kv_heads, row_bytes, \
-      num_blocks, block_size, st)
+  launch_pdl(store_table_kernel<VB>, dim3((unsigned)num_tokens), dim3(128), 0, s, (const char*)key_states,         \
+             (const char*)value_states, (char*)key_cache, (char*)value_cache, block_table, table_stride,           \
+             max_blocks_per_seq, cu_q_lens, context_kv_lens, num_seqs, num_tokens, num_kv_heads, row_bytes,         \
+             num_blocks, block_size, st)
   switch (vb) {
     case 16: LAUNCH(16); break;
     case 8: LAUNCH(8); break;

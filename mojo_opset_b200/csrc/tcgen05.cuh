@@ -204,24 +204,31 @@ __device__ __forceinline__ void umma_ss_x8_pair(uint32_t d_tmem, uint64_t a_desc
   MOJO_UMMA_SS_X8("2");
 }
 #undef MOJO_UMMA_SS_X8
-//   QK with head_dim 64: the four K-steps of the single 64-column half
+//   the four K-steps of ONE 64-column (128-byte) K-block: QK with head_dim 64, the GEMM main loop
+#define MOJO_UMMA_SS_X4(CTA)                                                                                        \
+  asm volatile(                                                                                                     \
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"                                                             \
+      "elect.sync _|q, 0xffffffff;\n\t"                                                                             \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                                   \
+      "setp.eq.b32 t, 0, 0;\n\t"                                                                                    \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], %1, %2, %3, p;\n\t"                                        \
+      "add.s64 a, %1, 2;\n\tadd.s64 b, %2, 2;\n\t"                                                                  \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, %1, 4;\n\tadd.s64 b, %2, 4;\n\t"                                                                  \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t"                                          \
+      "add.s64 a, %1, 6;\n\tadd.s64 b, %2, 6;\n\t"                                                                  \
+      "@q tcgen05.mma.cta_group::" CTA ".kind::f16 [%0], a, b, %3, t;\n\t}"                                         \
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)                                                 \
+      : "memory")
 __device__ __forceinline__ void umma_ss_x4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                            uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.eq.b32 t, 0, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "add.s64 a, %1, 2;\n\tadd.s64 b, %2, 2;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
-      "add.s64 a, %1, 4;\n\tadd.s64 b, %2, 4;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
-      "add.s64 a, %1, 6;\n\tadd.s64 b, %2, 6;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
+  MOJO_UMMA_SS_X4("1");
 }
+__device__ __forceinline__ void umma_ss_x4_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t acc) {
+  MOJO_UMMA_SS_X4("2");
+}
+#undef MOJO_UMMA_SS_X4
 //   PV: A = 8 TMEM columns per K-step (+8), B MN-major (+b_step/16 per 16 keys)
 #define MOJO_UMMA_TS_X8(CTA)                                                                                        \
   asm volatile(                                                                                                     \
