@@ -3,26 +3,32 @@
 // runs as soon as a tile's partials have landed, and a broadcast of the reduced tile into every rank's memory.
 // Reference semantics: mojo_opset/core/operators/compute_with_comm.py:57-117 (F.linear then all_reduce(sum)).
 //
-// Roles of a CTA (192 threads, one CTA per SM, persistent over tiles t = blockIdx.x, +gridDim.x, ...):
-//   warp 0     TMA producer: A [128 x 64] and B [128 x 64] slabs (K-major, 128B swizzle) through a 5-stage ring
-//   warp 1     MMA issuer: tcgen05.mma M128 N128 K16, fp32 accumulators in TMEM, two accumulator buffers so the
+// Roles of a CTA (192 threads, one CTA per SM, persistent over 128 x 128 output tiles; with >= 2 row blocks the CTAs
+// run as pairs, see the kernel):
+//   warp 0     TMA producer: A [128 x 64] and B [128 | 64 x 64] slabs (K-major, 128B swizzle) through a 5/7-stage ring
+//   warp 1     MMA issuer: tcgen05.mma M128/256 N128 K16, fp32 accumulators in TMEM, two accumulator buffers so the
 //              epilogue of tile i overlaps the main loop of tile i+1; TMEM allocation
-//   warps 2-5  epilogue: TMEM -> (+bias) -> bf16 -> swizzled 32 KB tile image in shared memory, then
-//                world == 1: image -> out (coalesced);
-//                world  > 1: ONE cp.async.bulk of the image into the owner's partial slot [tile][src rank] in
-//                            PEER memory (NVLink), system fence, epoch flag at the owner.
-//              after the CTA's last GEMM tile the same warps run (two-shot all-reduce, every CTA takes part):
-//                reduce units (owned tile, row slab): wait for the `world` partial flags, bulk-load the slabs into
-//                  shared memory, sum them in fp32 in rank order (deterministic, bit-identical on every rank),
-//                  bulk-store the bf16 slab into the result image of EVERY rank, flag each rank;
-//                copy units (tile): wait for the `world` slab flags, bulk-load the result image, un-swizzle it
-//                  into `out` (coalesced).
+//   warps 2-5  epilogue, one thread per tile row: TMEM -> (+bias) -> bf16 -> the row's 64 packed words, then
+//                world == 1: swizzled tile image in shared memory -> out (coalesced);
+//                world  > 1: the row goes out as 22 self-validating 16-byte LINES (3 payload words + the call's
+//                            epoch, ONE 128-bit store each - st.relaxed.sys.b128 is single-copy atomic, so a line is
+//                            seen whole or not at all) straight from registers into PEER memory: two-shot = the tile
+//                            owner's partial slot [tile][src rank]; one-shot = every rank's slot.  No bulk copy to
+//                            wait for, no fence, no separate flag: a reader polls the lines themselves.  (The first
+//                            version moved 32 KB images with cp.async.bulk + wait + system fence + flag per hop:
+//                            ~15 us of synchronisation around ~9 us of NVLink time at TP8.)  Lines cost 4/3 of the
+//                            bytes; rows past m are neither written nor read.
+//              after the CTA's last GEMM tile the same warps run (every CTA takes part):
+//                two-shot: reduce units (owned tile, slab of lines): poll the `world` partial lines, sum them in fp32 in
+//                  rank order (deterministic, bit-identical on every rank), store the result line into the result slot
+//                  of EVERY rank; copy units (tile): poll the result lines of a row, image -> out (coalesced);
+//                one-shot: poll the `world` partial lines of a row, sum in rank order, image -> out.
 //
-// No wait ever blocks a GEMM tile (all of a CTA's tiles are computed and pushed before its first wait), so the
-// protocol cannot deadlock however the ranks' CTAs are scheduled; every wait is time-bounded (trap after 5 s
-// instead of a hung GPU).  Flags carry the call's epoch and the buffers alternate with its parity, so nothing
-// is ever reset: rank A can only start call n+2 after every rank finished the reduce step of call n+1, hence
-// after every rank's kernel of call n - the last reader of the parity it is about to overwrite - has completed.
+// No wait ever blocks a GEMM tile (all of a CTA's tiles are computed and pushed before its first poll), so the
+// protocol cannot deadlock however the ranks' CTAs are scheduled; every poll is time-bounded (trap instead of a hung
+// GPU).  Lines carry the call's epoch and the slots alternate with its parity, so nothing is ever reset: rank A can
+// only start call n+2 after every rank finished the reduce step of call n+1, hence after every rank's kernel of call
+// n - the last reader of the parity it is about to overwrite - has completed.
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -50,8 +56,15 @@ static_assert((size_t)kStagesPair * (kSlabBytes + kSlabBytes / 2) >= (size_t)kSt
 // 600, 0 = wait for ever like NCCL): ranks of an eager serving loop may skew by seconds (GC pause, first-call module load)
 constexpr unsigned long long kDefaultWaitTimeoutNs = 600ull * 1000000000ull;
 constexpr size_t kHeaderBytes = 256;
+// a tile row (128 columns = 64 packed words) as 16-byte lines of 3 words + epoch; line (j, row) sits at index
+// j * 128 + row of the tile's slot, so the 32 rows of a warp store / load 512 contiguous bytes
+constexpr int kRowLines = 22;
+constexpr int kTileLines = kRowLines * kBM;
+constexpr int kTileLLBytes = kTileLines * 16;   // 45056
 constexpr int kOneShotMaxTiles = 128;                       // one-shot mode: every rank holds every rank's tile
-constexpr size_t kOneShotMaxPeerBytes = 6u << 20;           // ... so it is used while (world-1) * m * n * 2 B is small
+// ... so it is used only while (world-1) * m * n * 2 B is small.  Measured with the line protocol (8 GPUs, n 8192,
+// k 1024): m 16: two-shot 20.1 us / one-shot 24.4; m 64: 19.2 / 35.1; m 256: 30.2 / 88.2; (2 GPUs, k 4096) m 256: 37.0 / 39.8
+constexpr size_t kOneShotMaxPeerBytes = 512u << 10;
 
 struct Params {
   void* out;
@@ -62,10 +75,10 @@ struct Params {
   int owned_cap;    // partial slots per parity = ceil(max tiles / world)
   int tiles_cap;    // result images per parity = max tiles
   uint8_t* ws[kMaxWorld];  // workspace base of every rank as mapped HERE (ws[rank] is local memory)
-  size_t off_partial, off_result, off_flag_partial, off_flag_result;
+  size_t off_partial, off_result;
   int n_pair_tiles;  // PAIR: work items of a 2-CTA cluster = (256-row block, 128-column block)
-  int one_shot, one_cap;  // one-shot mode: slots [parity][tile < one_cap][src], flags alike
-  size_t off_one, off_flag_one;
+  int one_shot, one_cap;  // one-shot mode: slots [parity][tile < one_cap][src]
+  size_t off_one;
   unsigned long long timeout_ns;  // 0 = never give up
   int prefetch;       // B slabs pulled into L2 ahead of the ring (MOJO_B200_GAR_PREFETCH, k-blocks; 0 = off)
   long long* trace;   // developer timeline (MOJO_GAR_TRACE builds only, tools/gar_trace.py)
@@ -84,7 +97,7 @@ struct Params {
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_partial, off_result, off_flag_partial, off_flag_result, off_one, off_flag_one, total;
+  size_t off_partial, off_result, off_one, total;
   int owned_cap, tiles_cap, one_cap;
 };
 
@@ -94,34 +107,21 @@ inline Layout make_layout(int64_t max_m, int64_t n, int world) {
   l.tiles_cap = (int)tiles;
   l.owned_cap = (int)((tiles + world - 1) / world);
   l.off_partial = kHeaderBytes;  // [0] epoch counter, [4] finished-CTA counter
-  l.off_result = l.off_partial + (size_t)2 * l.owned_cap * world * kImageBytes;
-  l.off_flag_partial = l.off_result + (size_t)2 * l.tiles_cap * kImageBytes;
-  l.off_flag_result = align_up(l.off_flag_partial + (size_t)2 * l.owned_cap * world * 4, 256);
+  l.off_result = l.off_partial + (size_t)2 * l.owned_cap * world * kTileLLBytes;
   l.one_cap = l.tiles_cap < kOneShotMaxTiles ? l.tiles_cap : kOneShotMaxTiles;
-  l.off_flag_one = align_up(l.off_flag_result + (size_t)2 * l.tiles_cap * world * 4, 256);
-  l.off_one = align_up(l.off_flag_one + (size_t)2 * l.one_cap * world * 4, 1024);
-  l.total = align_up(l.off_one + (size_t)2 * l.one_cap * world * kImageBytes, 256);
+  l.off_one = l.off_result + (size_t)2 * l.tiles_cap * kTileLLBytes;
+  l.total = align_up(l.off_one + (size_t)2 * l.one_cap * world * kTileLLBytes, 256);
   return l;
 }
 
 __device__ __forceinline__ size_t partial_off(const Params& p, uint32_t par, int local_tile, int src) {
-  return p.off_partial + (((size_t)par * p.owned_cap + local_tile) * p.world + src) * kImageBytes;
+  return p.off_partial + (((size_t)par * p.owned_cap + local_tile) * p.world + src) * kTileLLBytes;
 }
 __device__ __forceinline__ size_t result_off(const Params& p, uint32_t par, int tile) {
-  return p.off_result + ((size_t)par * p.tiles_cap + tile) * kImageBytes;
+  return p.off_result + ((size_t)par * p.tiles_cap + tile) * kTileLLBytes;
 }
-__device__ __forceinline__ size_t flag_partial_off(const Params& p, uint32_t par, int local_tile, int src) {
-  return p.off_flag_partial + (((size_t)par * p.owned_cap + local_tile) * p.world + src) * 4;
-}
-__device__ __forceinline__ size_t flag_result_off(const Params& p, uint32_t par, int tile, int slab) {
-  return p.off_flag_result + (((size_t)par * p.tiles_cap + tile) * p.world + slab) * 4;
-}
-
 __device__ __forceinline__ size_t one_off(const Params& p, uint32_t par, int tile, int src) {
-  return p.off_one + (((size_t)par * p.one_cap + tile) * p.world + src) * kImageBytes;
-}
-__device__ __forceinline__ size_t flag_one_off(const Params& p, uint32_t par, int tile, int src) {
-  return p.off_flag_one + (((size_t)par * p.one_cap + tile) * p.world + src) * 4;
+  return p.off_one + (((size_t)par * p.one_cap + tile) * p.world + src) * kTileLLBytes;
 }
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
@@ -136,62 +136,49 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0,
                "r"(c1)
                : "memory");
 }
-// shared -> global (local or peer) bulk copy, tracked by the bulk async-group of the issuing thread
-__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-}
-// global (local memory, possibly written by peers) -> shared bulk copy completing on an mbarrier
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// order this thread's (acquired) view of global memory before its async-proxy reads of it
-__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ void st_flag_sys(uint32_t* flag, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+// one line = one 128-bit single-copy-atomic store / load at system scope (local or peer memory)
+__device__ __forceinline__ void st_line(void* dst, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t epoch) {
+  asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%1, %2};\n\tst.relaxed.sys.global.b128 [%0], t;\n\t}" ::"l"(dst),
+               "l"(((uint64_t)w1 << 32) | w0), "l"(((uint64_t)epoch << 32) | w2)
+               : "memory");
 }
-// several flags behind ONE system fence: fence + relaxed stores form the same release pattern as st.release per
-// flag, without paying a system-scope fence per destination rank
-__device__ __forceinline__ void st_flag_relaxed_sys(uint32_t* flag, uint32_t v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* flag) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-  return v;
+__device__ __forceinline__ uint4 ld_line(const void* src) {
+  uint64_t lo, hi;
+  asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.sys.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
+               : "=l"(lo), "=l"(hi)
+               : "l"(src)
+               : "memory");
+  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));  // .w = epoch
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, unsigned long long timeout_ns) {
-  if (ld_flag_sys(flag) == epoch) return;
-  const unsigned long long t0 = global_ns();
-  while (ld_flag_sys(flag) != epoch) {
-    __nanosleep(40);
-    if (timeout_ns && global_ns() - t0 > timeout_ns) __trap();  // a peer never arrived: launch failure, not a hung GPU
+// bookkeeping of a polling loop: backs off a little, and a peer that never arrives becomes a launch failure (trap)
+// after timeout_ns instead of a hung GPU
+struct PollGuard {
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  __device__ __forceinline__ void miss(unsigned long long timeout_ns) {
+    __nanosleep(20);
+    if ((++spins & 255u) == 0 && timeout_ns) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > timeout_ns) __trap();
+    }
   }
-}
-// L2-coherent 16-byte load (peers wrote this memory: never take a stale L1 line)
-__device__ __forceinline__ uint4 ld_cg(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
+};
 // byte offset of 16-byte chunk `c` (8 elements) of row `r` inside a tile image: rows of 256 B, chunk index XOR-ed
 // with the row so that the per-row epilogue stores are bank-conflict free
 __device__ __forceinline__ uint32_t image_off(uint32_t r, uint32_t c) { return r * 256u + ((c ^ (r & 7u)) << 4); }
 
-template <typename T> __device__ __forceinline__ void acc2(float (&a)[8], const uint4& v) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// the three payload words of a line (6 sixteen-bit values) added to six fp32 sums
+template <typename T> __device__ __forceinline__ void acc_line(float (&a)[6], const uint4& v) {
+  const uint32_t w[3] = {v.x, v.y, v.z};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (std::is_same<T, __nv_bfloat16>::value) {
       a[2 * i] += __uint_as_float(w[i] << 16);
       a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
@@ -199,6 +186,118 @@ template <typename T> __device__ __forceinline__ void acc2(float (&a)[8], const 
       const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
       a[2 * i] += f.x;
       a[2 * i + 1] += f.y;
+    }
+  }
+}
+
+// Two-shot reduce unit: lines [slab * LPS, +LPS) of owned tile `t` (LPS = 2816 / WORLD).  A thread takes 16 / WORLD
+// lines per pass - all `WORLD` sources of all of them requested before the first is looked at - polls until every line
+// carries this call's epoch, sums in rank order and stores the result line into the result slot of every rank.
+template <typename T, int WORLD>
+__device__ __forceinline__ void ll_reduce_unit(const Params& p, uint32_t par, uint32_t epoch, int local_tile, int t,
+                                               int slab, int tid) {
+  constexpr int LPS = kTileLines / WORLD;
+  constexpr int LPB = 16 / WORLD;
+  const int tm = t / p.tiles_n;
+  const int rows_valid = (int)(p.m - (int64_t)tm * kBM < kBM ? p.m - (int64_t)tm * kBM : kBM);
+  const uint8_t* src0 = p.ws[p.rank] + partial_off(p, par, local_tile, 0);
+  const size_t dst_off = result_off(p, par, t);
+  const int l_end = (slab + 1) * LPS;
+#pragma unroll 1
+  for (int l0 = slab * LPS + tid; l0 < l_end; l0 += kEpiThreads * LPB) {
+    uint4 v[LPB][WORLD];
+    bool act[LPB];
+#pragma unroll
+    for (int i = 0; i < LPB; ++i) {
+      const int line = l0 + i * kEpiThreads;
+      act[i] = line < l_end && (line & (kBM - 1)) < rows_valid;  // (line = j * 128 + row)
+    }
+    PollGuard guard;
+    for (;;) {
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < LPB; ++i) {
+        if (act[i]) {
+#pragma unroll
+          for (int sr = 0; sr < WORLD; ++sr)
+            v[i][sr] = ld_line(src0 + (size_t)sr * kTileLLBytes + ((size_t)(l0 + i * kEpiThreads) << 4));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < LPB; ++i) {
+        if (act[i]) {
+#pragma unroll
+          for (int sr = 0; sr < WORLD; ++sr) ok = ok && v[i][sr].w == epoch;
+        }
+      }
+      if (ok) break;
+      guard.miss(p.timeout_ns);
+    }
+#pragma unroll
+    for (int i = 0; i < LPB; ++i) {
+      if (act[i]) {
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sr = 0; sr < WORLD; ++sr) acc_line<T>(acc, v[i][sr]);
+        const uint32_t w0 = pack2<T>(acc[0], acc[1]), w1 = pack2<T>(acc[2], acc[3]), w2 = pack2<T>(acc[4], acc[5]);
+        const size_t off = dst_off + ((size_t)(l0 + i * kEpiThreads) << 4);
+#pragma unroll
+        for (int d = 0; d < WORLD; ++d) st_line(p.ws[d] + off, w0, w1, w2, epoch);
+      }
+    }
+  }
+}
+
+// The 22 lines of tile row `row` from NSRC slots (slot s at src0 + s * kTileLLBytes), summed in slot order (NSRC = 1:
+// taken as they are), into the swizzled tile image in shared memory.  One-shot: NSRC = world partial slots; two-shot
+// copy: NSRC = 1, the result slot.
+template <typename T, int NSRC>
+__device__ __forceinline__ void ll_gather_row(const Params& p, const uint8_t* src0, uint32_t epoch, int row, uint8_t* image) {
+  constexpr int LPB = NSRC >= 8 ? 2 : (NSRC == 4 ? 4 : (NSRC == 2 ? 8 : 11));
+#pragma unroll 1
+  for (int j0 = 0; j0 < kRowLines; j0 += LPB) {
+    uint4 v[LPB][NSRC];
+    PollGuard guard;
+    for (;;) {
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < LPB; ++i) {
+        if (j0 + i < kRowLines) {
+#pragma unroll
+          for (int sr = 0; sr < NSRC; ++sr)
+            v[i][sr] = ld_line(src0 + (size_t)sr * kTileLLBytes + ((size_t)((j0 + i) * kBM + row) << 4));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < LPB; ++i) {
+        if (j0 + i < kRowLines) {
+#pragma unroll
+          for (int sr = 0; sr < NSRC; ++sr) ok = ok && v[i][sr].w == epoch;
+        }
+      }
+      if (ok) break;
+      guard.miss(p.timeout_ns);
+    }
+#pragma unroll
+    for (int i = 0; i < LPB; ++i) {
+      const int j = j0 + i;
+      if (j < kRowLines) {
+        uint32_t w[3];
+        if (NSRC == 1) {
+          w[0] = v[i][0].x; w[1] = v[i][0].y; w[2] = v[i][0].z;
+        } else {
+          float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int sr = 0; sr < NSRC; ++sr) acc_line<T>(acc, v[i][sr]);
+          w[0] = pack2<T>(acc[0], acc[1]); w[1] = pack2<T>(acc[2], acc[3]); w[2] = pack2<T>(acc[4], acc[5]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int widx = 3 * j + k;  // packed word of the row: columns 2 widx, 2 widx + 1
+          if (widx < kBN / 2)
+            *reinterpret_cast<uint32_t*>(image + image_off((uint32_t)row, (uint32_t)(widx >> 2)) + (widx & 3) * 4) = w[k];
+        }
+      }
     }
   }
 }
@@ -224,8 +323,7 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
   uint64_t* empty = bars + kStg;            // [kStg]
   uint64_t* acc_full = empty + kStg;        // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint64_t* aux_bar = acc_empty + 2;        // bulk loads of the reduce / copy phases
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint32_t* epoch_slot = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,7 +350,6 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
-    mbar_init(aux_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -407,6 +504,7 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
         if (lane == 0) mbar_arrive_cluster(lead_acc_empty + (uint32_t)a * 8u);
         continue;
       }
+      uint32_t words[kBN / 2];  // this thread's row of the tile, two 16-bit values per word
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         uint32_t r[32];
@@ -423,12 +521,8 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
             for (int i = 0; i < 8; ++i)
               if (gc + i < p.n) f[i] += DType<T>::to_f(bias[gc + i]);
           }
-          uint4 v;
-          v.x = pack2<T>(f[0], f[1]);
-          v.y = pack2<T>(f[2], f[3]);
-          v.z = pack2<T>(f[4], f[5]);
-          v.w = pack2<T>(f[6], f[7]);
-          *reinterpret_cast<uint4*>(image + image_off(row, c4 * 4 + g)) = v;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) words[c4 * 16 + g * 4 + i] = pack2<T>(f[2 * i], f[2 * i + 1]);
         }
       }
       tc_fence_before();
@@ -437,145 +531,75 @@ gemm_allreduce_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_co
         if (PAIR) mbar_arrive_cluster(lead_acc_empty + (uint32_t)a * 8u); else mbar_arrive(&acc_empty[a]);
       }
       if (p.world == 1) {
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch)
+          *reinterpret_cast<uint4*>(image + image_off(row, ch)) =
+              make_uint4(words[4 * ch], words[4 * ch + 1], words[4 * ch + 2], words[4 * ch + 3]);
         epi_barrier();
         image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(image + off); }, tm, tn);
         epi_barrier();
         if (tid == 0) GTRACE(2, 2 + 2 * it);
-      } else {
-        fence_async_smem();
-        epi_barrier();
-        if (tid == 0) {
-          if (p.one_shot) {
-            for (int d = 0; d < p.world; ++d) bulk_store(p.ws[d] + one_off(p, par, t, p.rank), image, kImageBytes);
-            tma_store_commit();
-            tma_store_wait_all();  // image read and the peer writes performed
-            __threadfence_system();
-            for (int d = 0; d < p.world; ++d)
-              st_flag_relaxed_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_one_off(p, par, t, p.rank)), epoch);
-          } else {
-            const int owner = t % p.world, local_tile = t / p.world;
-            bulk_store(p.ws[owner] + partial_off(p, par, local_tile, p.rank), image, kImageBytes);
-            tma_store_commit();
-            tma_store_wait_all();
-            st_flag_sys(reinterpret_cast<uint32_t*>(p.ws[owner] + flag_partial_off(p, par, local_tile, p.rank)), epoch);
+      } else if ((int64_t)tm * kBM + row < p.m) {
+        // the row leaves as 22 lines, each ONE 128-bit store that carries its own validity (the epoch): nothing to
+        // wait for, nothing to fence, no flag to raise
+        const size_t line0 = (size_t)row << 4;
+        if (p.one_shot) {
+          const size_t off = one_off(p, par, t, p.rank) + line0;
+          for (int d = 0; d < p.world; ++d) {
+            uint8_t* dst = p.ws[d] + off;
+#pragma unroll
+            for (int j = 0; j < kRowLines; ++j)
+              st_line(dst + (size_t)j * (kBM * 16), words[3 * j], 3 * j + 1 < kBN / 2 ? words[3 * j + 1] : 0u,
+                      3 * j + 2 < kBN / 2 ? words[3 * j + 2] : 0u, epoch);
           }
+        } else {
+          uint8_t* dst = p.ws[t % p.world] + partial_off(p, par, t / p.world, p.rank) + line0;
+#pragma unroll
+          for (int j = 0; j < kRowLines; ++j)
+            st_line(dst + (size_t)j * (kBM * 16), words[3 * j], 3 * j + 1 < kBN / 2 ? words[3 * j + 1] : 0u,
+                    3 * j + 2 < kBN / 2 ? words[3 * j + 2] : 0u, epoch);
         }
-        epi_barrier();  // the image buffer is free again
       }
     }
 
     if (p.world > 1 && p.one_shot) {
-      // ---- one-shot: every rank holds every rank's partial of every tile; this CTA sums the tiles it computed
-      // straight into `out`.  The operand ring is free (see below) and stages `world` row chunks at a time.
-      uint8_t* self = p.ws[p.rank];
-      uint32_t aux_phase = 0;
-      const int rows_per_pass = p.world <= 4 ? kBM : kBM / 2;  // world * chunk <= 128 KB of the ring
-      const uint32_t chunk_bytes = rows_per_pass * 256;
+      // ---- one-shot: every rank holds every rank's partial lines of every tile; tile t is summed straight into `out`
+      // by CTA t % grid (a thread per row: poll the `world` slots' lines, sum in rank order, image -> out)
+      const uint8_t* self = p.ws[p.rank];
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-        if (tid < p.world) wait_flag(reinterpret_cast<const uint32_t*>(self + flag_one_off(p, par, t, tid)), epoch, p.timeout_ns);
-        epi_barrier();
-        for (int r0 = 0; r0 < kBM; r0 += rows_per_pass) {
-          if (tid == 0) {
-            fence_async_global();
-            mbar_expect_tx(aux_bar, chunk_bytes * p.world);
-            for (int s = 0; s < p.world; ++s)
-              bulk_load(ring + s * chunk_bytes, self + one_off(p, par, t, s) + r0 * 256, chunk_bytes, aux_bar);
+        if ((int64_t)tm * kBM + row < p.m) {
+          const uint8_t* src0 = self + one_off(p, par, t, 0);
+          switch (p.world) {
+            case 2: ll_gather_row<T, 2>(p, src0, epoch, row, image); break;
+            case 4: ll_gather_row<T, 4>(p, src0, epoch, row, image); break;
+            default: ll_gather_row<T, 8>(p, src0, epoch, row, image); break;
           }
-          mbar_wait_bounded(aux_bar, aux_phase);
-          aux_phase ^= 1u;
-#pragma unroll 2
-          for (int idx = tid; idx < rows_per_pass * 16; idx += kEpiThreads) {
-            const int r = r0 + (idx >> 4), ch = idx & 15;
-            const int64_t gr = (int64_t)tm * kBM + r, gc = (int64_t)tn * kBN + ch * 8;
-            if (gr < p.m && gc < p.n) {
-              const uint32_t off = image_off(r, ch) - r0 * 256;
-              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int s = 0; s < kMaxWorld; ++s)
-                if (s < p.world) acc2<T>(acc, *reinterpret_cast<const uint4*>(ring + s * chunk_bytes + off));
-              uint4 v;
-              v.x = pack2<T>(acc[0], acc[1]);
-              v.y = pack2<T>(acc[2], acc[3]);
-              v.z = pack2<T>(acc[4], acc[5]);
-              v.w = pack2<T>(acc[6], acc[7]);
-              T* dst = out + gr * p.out_rs + gc;
-              if (gc + 8 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                *reinterpret_cast<uint4*>(dst) = v;
-              } else {
-                const T* e = reinterpret_cast<const T*>(&v);
-                for (int i = 0; i < 8 && gc + i < p.n; ++i) dst[i] = e[i];
-              }
-            }
-          }
-          epi_barrier();  // the ring chunk buffers are free again
         }
+        epi_barrier();
+        image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(image + off); }, tm, tn);
+        epi_barrier();  // the image is free again
       }
     } else if (p.world > 1) {
-      // every MMA that read the operand ring has completed (the last acc_full commit was observed above) and the
-      // producer has nothing left to load: the ring is free, its first 64 KB stage the bulk loads below
-      uint8_t* self = p.ws[p.rank];
-      uint8_t* red_in = ring;                 // `world` partial slabs (32 KB in total)
-      uint8_t* copy_in = ring + kImageBytes;  // one result image
-      uint32_t aux_phase = 0;
-      // ---- reduce units: (owned tile, row slab); unit u of this rank goes to CTA u % gridDim.x
+      // ---- two-shot, reduce units: (owned tile, slab of lines); unit u of this rank goes to CTA u % grid
       const int owned = (p.n_tiles - p.rank + p.world - 1) / p.world;  // tiles t with t % world == rank
-      const uint32_t slab_bytes = kImageBytes / p.world;
       for (int u = blockIdx.x; u < owned * p.world; u += gridDim.x) {
         const int local_tile = u / p.world, slab = u - local_tile * p.world;
         const int t = local_tile * p.world + p.rank;
-        if (tid < p.world)
-          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_partial_off(p, par, local_tile, tid)), epoch, p.timeout_ns);
-        epi_barrier();
-        if (tid == 0) {
-          fence_async_global();
-          mbar_expect_tx(aux_bar, kImageBytes);
-          for (int s = 0; s < p.world; ++s)
-            bulk_load(red_in + s * slab_bytes, self + partial_off(p, par, local_tile, s) + slab * slab_bytes, slab_bytes,
-                      aux_bar);
+        switch (p.world) {
+          case 2: ll_reduce_unit<T, 2>(p, par, epoch, local_tile, t, slab, tid); break;
+          case 4: ll_reduce_unit<T, 4>(p, par, epoch, local_tile, t, slab, tid); break;
+          default: ll_reduce_unit<T, 8>(p, par, epoch, local_tile, t, slab, tid); break;
         }
-        mbar_wait_bounded(aux_bar, aux_phase);
-        aux_phase ^= 1u;
-        for (uint32_t off = tid * 16; off < slab_bytes; off += kEpiThreads * 16) {
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int s = 0; s < kMaxWorld; ++s)
-            if (s < p.world) acc2<T>(acc, *reinterpret_cast<const uint4*>(red_in + s * slab_bytes + off));
-          uint4 o;
-          o.x = pack2<T>(acc[0], acc[1]);
-          o.y = pack2<T>(acc[2], acc[3]);
-          o.z = pack2<T>(acc[4], acc[5]);
-          o.w = pack2<T>(acc[6], acc[7]);
-          *reinterpret_cast<uint4*>(image + off) = o;
-        }
-        fence_async_smem();
-        epi_barrier();
-        if (tid == 0) {
-          const size_t dst = result_off(p, par, t) + (size_t)slab * slab_bytes;
-          for (int d = 0; d < p.world; ++d) bulk_store(p.ws[d] + dst, image, slab_bytes);
-          tma_store_commit();
-          tma_store_wait_all();
-          __threadfence_system();
-          for (int d = 0; d < p.world; ++d)
-            st_flag_relaxed_sys(reinterpret_cast<uint32_t*>(p.ws[d] + flag_result_off(p, par, t, slab)), epoch);
-        }
-        epi_barrier();  // image and red_in are free again
       }
-      // ---- copy units: the tiles this CTA computed
+      // ---- copy units: tile t by CTA t % grid (a thread per row: poll the result lines, image -> out)
+      const uint8_t* self = p.ws[p.rank];
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-        if (tid < p.world)
-          wait_flag(reinterpret_cast<const uint32_t*>(self + flag_result_off(p, par, t, tid)), epoch, p.timeout_ns);
+        if ((int64_t)tm * kBM + row < p.m) ll_gather_row<T, 1>(p, self + result_off(p, par, t), epoch, row, image);
         epi_barrier();
-        if (tid == 0) {
-          fence_async_global();
-          mbar_expect_tx(aux_bar, kImageBytes);
-          bulk_load(copy_in, self + result_off(p, par, t), kImageBytes, aux_bar);
-        }
-        mbar_wait_bounded(aux_bar, aux_phase);
-        aux_phase ^= 1u;
-        image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(copy_in + off); }, tm, tn);
-        epi_barrier();
+        image_to_out([&](uint32_t off) { return *reinterpret_cast<const uint4*>(image + off); }, tm, tn);
+        epi_barrier();  // the image is free again
       }
     }
   }
@@ -736,8 +760,7 @@ extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const
                  workspace_bytes, l.total);
     p.owned_cap = l.owned_cap; p.tiles_cap = l.tiles_cap;
     p.off_partial = l.off_partial; p.off_result = l.off_result;
-    p.off_flag_partial = l.off_flag_partial; p.off_flag_result = l.off_flag_result;
-    p.one_cap = l.one_cap; p.off_one = l.off_one; p.off_flag_one = l.off_flag_one;
+    p.one_cap = l.one_cap; p.off_one = l.off_one;
     // one-shot (push to everyone, reduce locally: one NVLink hop) while the extra traffic is cheap; two-shot
     // (push to the owner, reduce, broadcast: two hops, 1/world of the bytes per hop) beyond
     const char* mode = getenv("MOJO_B200_GAR_MODE");  // "one" / "two" force a mode (both ranks alike!)

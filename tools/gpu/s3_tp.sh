@@ -1,6 +1,6 @@
 #!/bin/bash
-# TP step A/B at N GPUs: PDL / pair / prefetch variants of the fused GEMM + all-reduce
-N=${1:-2}
+# TP step at N GPUs (tp_cfg4 leg only) + the stand-alone fused GEMM + all-reduce bench; extra args: variants to run
+N=${1:-2}; shift
 mkdir -p gpurun_out
 run() { # name, env...
   name=$1; shift
@@ -9,8 +9,15 @@ run() { # name, env...
 }
 rm -f gpurun_out/s3_tp_n$N.jsonl
 run base X=1
-run nopdl MOJO_B200_PDL=0
-run nopair MOJO_B200_GAR_PAIR=0
-run pf12 MOJO_B200_GAR_PREFETCH=12
-run pfall MOJO_B200_GAR_PREFETCH=100000
+for v in "$@"; do
+  case $v in
+    nopdl) run nopdl MOJO_B200_PDL=0;;
+    nopair) run nopair MOJO_B200_GAR_PAIR=0;;
+    two) run two MOJO_B200_GAR_MODE=two;;
+    one) run one MOJO_B200_GAR_MODE=one;;
+  esac
+done
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 tools/bench_gemm_allreduce.py --check --steps 20 --warmup 5 2>gpurun_out/s3_gar_n$N.err | tail -3 | tee gpurun_out/s3_gar_n$N.txt | cut -c1-900
+for tok in 16 64; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29537 tools/bench_gemm_allreduce.py --tokens $tok --steps 20 --warmup 5 2>>gpurun_out/s3_gar_n$N.err | tail -1 | tee -a gpurun_out/s3_gar_n$N.txt | cut -c1-700
+done
