@@ -8,9 +8,19 @@
 // CTA carries 256 / TPR rows, so every thread has 4 (8 with a residual) independent 16-byte loads in flight
 // before the reduction.  Each thread keeps its slice of the row in registers between the reduction and the
 // scaling, so x / residual are read exactly once: bytes = (2 reads + 2 writes) * rows * H * sizeof(T) + H.
-#include "common.cuh"
+#include <type_traits>
+
+#include "tcgen05.cuh"  // packed fp32x2 arithmetic (mul.rn.f32x2 / add.rn.f32x2 round each lane like the scalar op)
 
 namespace mojo {
+
+template <typename T> __device__ __forceinline__ float2 rn_unpack_pair(uint32_t w) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  } else {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  }
+}
 
 constexpr int kMaxVecsPerThread = 4;  // register-resident slice: up to 4 x 16 B per thread
 
@@ -40,8 +50,10 @@ __global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kerne
   const bool active = row < rows;
   const int vecs = hidden / N;
 
+  constexpr bool kPacked = sizeof(T) == 2 && VEC % 2 == 0;
   PackN<T, VEC> keep[kMaxVecsPerThread];
   float ss = 0.f;
+  float2 ss2 = make_float2(0.f, 0.f);
   if (active) {
     const T* xr = x + row * x_rs;
     const T* rr = HAS_RES ? res + row * res_rs : nullptr;
@@ -50,6 +62,24 @@ __global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kerne
       const int v = lane_in_row + i * TPR;
       if (v < vecs) {
         PackN<T, VEC> a = ld_pack<T, VEC>(xr + (int64_t)v * N);
+        if constexpr (kPacked) {
+          // two elements per issue slot (FADD2 / FFMA2): the same roundings as the scalar form, lane by lane
+          uint32_t* aw = reinterpret_cast<uint32_t*>(&a);
+          PackN<T, VEC> b;
+          if (HAS_RES) b = ld_pack<T, VEC>(rr + (int64_t)v * N);
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+          for (int e = 0; e < N / 2; ++e) {
+            float2 f = rn_unpack_pair<T>(aw[e]);
+            if (HAS_RES) {
+              f = add2(f, rn_unpack_pair<T>(bw[e]));
+              aw[e] = pack2<T>(f.x, f.y);
+              f = rn_unpack_pair<T>(aw[e]);
+            }
+            ss2 = fma2(f, f, ss2);
+          }
+          keep[i] = a;
+        } else {
         if (HAS_RES) {
           const PackN<T, VEC> b = ld_pack<T, VEC>(rr + (int64_t)v * N);
 #pragma unroll
@@ -60,6 +90,7 @@ __global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kerne
         for (int e = 0; e < N; ++e) {
           const float f = DType<T>::to_f(a.v[e]);
           ss = fmaf(f, f, ss);
+        }
         }
       }
     }
@@ -80,6 +111,7 @@ __global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kerne
     }
   }
 
+  if constexpr (kPacked) ss += ss2.x + ss2.y;
   // reduce ss over the TPR threads of the row (fixed order: deterministic)
   if constexpr (TPR <= 32) {
 #pragma unroll
@@ -106,9 +138,21 @@ __global__ void __launch_bounds__(TPR > kNormCta ? TPR : kNormCta) rmsnorm_kerne
     if (v < vecs) {
       const PackN<T, VEC> g = ld_pack<T, VEC>(w + (int64_t)v * N);
       PackN<T, VEC> o;
+      if constexpr (kPacked) {
+        const uint32_t* kw = reinterpret_cast<const uint32_t*>(&keep[i]);
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g);
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+        for (int e = 0; e < N / 2; ++e) {
+          const float2 t = mul2(mul2(rn_unpack_pair<T>(kw[e]), inv2), rn_unpack_pair<T>(gw[e]));
+          ow[e] = pack2<T>(t.x, t.y);
+        }
+      } else {
 #pragma unroll
       for (int e = 0; e < N; ++e)
         o.v[e] = DType<T>::from_f(__fmul_rn(__fmul_rn(DType<T>::to_f(keep[i].v[e]), inv), DType<T>::to_f(g.v[e])));
+      }
       st_pack<T, VEC>(yr + (int64_t)v * N, o);
       if (HAS_RES && sum_out) st_pack<T, VEC>(sum_out + row * sum_rs + (int64_t)v * N, keep[i]);
     }

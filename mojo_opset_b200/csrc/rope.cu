@@ -12,7 +12,7 @@
 // to that dtype too.
 #include <type_traits>
 
-#include "common.cuh"
+#include "tcgen05.cuh"  // packed fp32x2 arithmetic: mul.rn.f32x2 / add.rn.f32x2 round each lane like the scalar op
 
 namespace mojo {
 
@@ -155,6 +155,21 @@ __global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs
     float x[VEC], y[VEC], r[VEC];
     unpack(o, x);
     unpack(xb, y);
+    if constexpr (VEC % 2 == 0) {  // two elements per issue slot (FMUL2 / FADD2), the scalar form's roundings lane by lane
+#pragma unroll
+      for (int e = 0; e < VEC; e += 2) {
+        float2 p = mul2(make_float2(x[e], x[e + 1]), make_float2(csf[e], csf[e + 1]));
+        float2 q = mul2(make_float2(y[e], y[e + 1]), make_float2(snf[e], snf[e + 1]));
+        if (ROUND_T) {
+          p = make_float2(round_through<T>(p.x), round_through<T>(p.y));
+          q = make_float2(round_through<T>(q.x), round_through<T>(q.y));
+        }
+        // scalar adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in the SASS; the products must be
+        // rounded before the sum to reproduce the reference bit for bit)
+        r[e] = __fadd_rn(p.x, q.x);
+        r[e + 1] = __fadd_rn(p.y, q.y);
+      }
+    } else {
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       float p = __fmul_rn(x[e], csf[e]), q = __fmul_rn(y[e], snf[e]);
@@ -163,6 +178,7 @@ __global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs
         q = round_through<T>(q);
       }
       r[e] = __fadd_rn(p, q);
+    }
     }
     if constexpr (sizeof(T) == 2 && VEC % 2 == 0) {
       uint32_t* w = reinterpret_cast<uint32_t*>(&o);
