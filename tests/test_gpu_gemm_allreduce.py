@@ -1,9 +1,12 @@
 """-m gpu: MojoGemmAllReduce (csrc/gemm_allreduce.cu) through the C ABI.
 
 * world == 1: the tcgen05 GEMM alone against the oracle (``F.linear`` semantics) over ragged shapes;
-* world in {2, 4, 8} on ONE GPU: the full push / reduce / broadcast protocol with `world` VIRTUAL ranks in this
+* world in {2, 4, 8} on ONE GPU: the full push / reduce / broadcast protocol (self-validating 16-byte lines: three
+  payload words + the call's epoch per 128-bit store, polled by the reader) with `world` VIRTUAL ranks in this
   process (``comm.LocalRanks``: one workspace and one stream per rank, plain pointers instead of IPC mappings),
-  several back-to-back calls so that both buffer parities and the epoch flags are exercised;
+  several back-to-back calls so that both slot parities and the epochs are exercised; shapes with one and with several
+  128-row blocks, so both the single-CTA and the CTA-pair (cta_group::2) GEMM run, ragged m / n (rows past m are
+  neither sent nor read);
 * >= 2 real GPUs (skipped otherwise): tools/bench_gemm_allreduce.py under torchrun, IPC + NVLink.
 """
 
