@@ -8,7 +8,7 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "tcgen05.cuh"  // packed fp32x2 arithmetic
+#include "common.cuh"
 
 namespace mojo {
 
@@ -55,26 +55,6 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
   return 0.5f * x * (x >= 0.f ? 2.0f - q : q);
 }
 
-// the same on a pair of elements: the polynomial, the scalings and the final products as FFMA2 / FMUL2 (one issue slot
-// for two elements; the kernel is issue-bound: ~17 instructions per element around its two MUFU operations)
-__device__ __forceinline__ float2 gelu_fast_f2(float2 x) {
-  const float2 z = mul2(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
-  const float2 den = fma2(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
-  const float2 arg = mul2(mul2(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
-  float2 t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
-  float2 q = fma2(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
-  q = fma2(q, t, make_float2(1.421413741f, 1.421413741f));
-  q = fma2(q, t, make_float2(-0.284496736f, -0.284496736f));
-  q = fma2(q, t, make_float2(0.254829592f, 0.254829592f));
-  q = mul2(mul2(q, t), e);  // erfc(z)
-  const float2 f = make_float2(x.x >= 0.f ? 2.0f - q.x : q.x, x.y >= 0.f ? 2.0f - q.y : q.y);
-  return mul2(mul2(x, make_float2(0.5f, 0.5f)), f);
-}
-
 template <typename T, bool GELU> __device__ __forceinline__ float unary_f(float x) {
   if constexpr (GELU) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value) return gelu_fast_f(x);
@@ -103,16 +83,6 @@ __global__ void __launch_bounds__(256, 4) act_kernel(const T* __restrict__ gate,
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     auto compute = [&](const Vec16<T>& gv, const Vec16<T>& uv) {
       Vec16<T> ov;
-      if constexpr (GELU && !GATED && std::is_same<T, __nv_bfloat16>::value) {
-        const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
-        uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-        for (int e = 0; e < N / 2; ++e) {
-          const float2 r = gelu_fast_f2(make_float2(__uint_as_float(gw[e] << 16), __uint_as_float(gw[e] & 0xffff0000u)));
-          ow[e] = pack2<T>(r.x, r.y);
-        }
-        return ov;
-      }
 #pragma unroll
       for (int e = 0; e < N; ++e) {
         float gf = DType<T>::to_f(gv.v[e]);
