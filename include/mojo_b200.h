@@ -275,14 +275,16 @@ MOJO_B200_API int mojo_b200_sdpa_masked(const void* query, const void* key, cons
  *                                     (fused precedent: backends/ttx/operators/compute_with_comm.py:102-167)
  *
  * out[m, n] = all_reduce_sum over `world` ranks of ( x[m, k] @ weight[n, k]^T + bias[n] )   (bias on every rank,
- * as the reference adds it before the all-reduce).  ONE persistent kernel: tcgen05 GEMM, partial tiles pushed
- * over NVLink into the tile owner's workspace, fp32 reduction in rank order (bit-identical on all ranks),
- * reduced tiles broadcast to every rank.  world == 1 is a plain GEMM (no workspace).
+ * as the reference adds it before the all-reduce).  ONE persistent kernel: tcgen05 GEMM (CTA pairs, cta_group::2,
+ * once there are two 128-row blocks), partial tile rows pushed over NVLink into the tile owner's workspace as
+ * self-validating 16-byte lines (3 payload words + the call's epoch, one 128-bit system-scope store each), fp32
+ * reduction in rank order (bit-identical on all ranks), reduced lines broadcast to every rank.  world == 1 is a plain
+ * GEMM (no workspace).  Launched with programmatic stream serialization (MOJO_B200_PDL=0 turns it off).
  *
  * The workspace is "symmetric": every rank allocates the same number of bytes with mojo_b200_symm_alloc
  * (cudaMalloc, zero-filled), exports it (64-byte CUDA IPC handle), exchanges handles out of band (the host side
  * uses torch.distributed) and opens its peers' handles; peer_workspaces[r] is rank r's workspace as mapped in
- * THIS process (peer_workspaces[rank] = the local allocation).  The call counter that versions the flags lives in
+ * THIS process (peer_workspaces[rank] = the local allocation).  The call counter (epoch) that versions the lines lives in
  * the workspace itself (device memory), so the launch is CUDA-graph replayable; all ranks must make the same
  * sequence of calls with the same m.  world must be 1, 2, 4 or 8.  x / weight rows must be 16-byte aligned; dtype bf16 / fp16.
  * ------------------------------------------------------------------------------------------------- */
