@@ -61,6 +61,13 @@ MOJO_B200_API int mojo_b200_device_ok(void);
 #define MOJO_B200_ERR_PREFILL_UNMAPPED_BLOCK 2
 MOJO_B200_API int mojo_b200_set_error_word(int* device_word);
 
+/* Split-KV decode (mojo_b200_paged_decode_gqa / _swa with more than one split): `count` ints of ZERO-INITIALISED device
+ * memory on the current device, used as arrival counters so that the last split of a (sequence, kv head) group folds
+ * the group's partials inside the main kernel (no second launch).  The kernels leave the words zero; a launch uses
+ * batch * num_kv_heads * ceil(group / 16) of them and consecutive launches rotate over up to 16 disjoint slices.
+ * Without a registration (or with too few words) the partials are folded by a second kernel.  NULL / 0 unregisters. */
+MOJO_B200_API int mojo_b200_set_decode_tickets(int* device_words, int64_t count);
+
 /* ---------------------------------------------------------------------------------------------------
  * MojoStorePagedKVCache.forward                     mojo_opset/core/operators/kv_cache.py:110-171
  *

@@ -33,6 +33,7 @@ SIGNATURES = {
     "mojo_b200_last_error": (c_char_p, []),
     "mojo_b200_device_ok": (I, []),
     "mojo_b200_set_error_word": (I, [P]),
+    "mojo_b200_set_decode_tickets": (I, [P, L]),
     "mojo_b200_store_paged_kv_chunks": (I, [P, P, P, P, P, L, L, I, I, L, I] + [L] * 10 + [I, P]),
     "mojo_b200_store_paged_kv_table": (I, [P, P, P, P, P, L, I, P, P, I, L, I, I, L, I] + [L] * 10 + [I, P]),
     "mojo_b200_rms_norm": (I, [P, P, P, L, I, L, L, F, I, P]),
@@ -132,6 +133,8 @@ def check(lib, rc: int, what: str) -> None:
 _error_words = {}
 
 ERR_DECODE_UNMAPPED_BLOCK, ERR_PREFILL_UNMAPPED_BLOCK = 1, 2
+DECODE_TICKETS = 1 << 16  # ints per device (256 KiB): 16 slices of 4096 (sequence, kv head) groups
+_decode_tickets = {}
 
 
 def error_word(device) -> torch.Tensor:
@@ -144,9 +147,13 @@ def error_word(device) -> torch.Tensor:
         if torch.cuda.is_current_stream_capturing():
             return None  # registered by the first eager call; kernels skip the check while there is no word
         word = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", index))
+        # ... and the split-KV decode's arrival counters (zero between launches: the kernels reset what they count)
+        tickets = torch.zeros(DECODE_TICKETS, dtype=torch.int32, device=torch.device("cuda", index))
         with torch.cuda.device(index):
             check(load(), load().mojo_b200_set_error_word(word.data_ptr()), "set_error_word")
+            check(load(), load().mojo_b200_set_decode_tickets(tickets.data_ptr(), DECODE_TICKETS), "set_decode_tickets")
         _error_words[index] = word
+        _decode_tickets[index] = tickets
     return word
 
 

@@ -28,6 +28,19 @@ int* error_word() {
   return g_error_word[dev];
 }
 
+// Arrival counters of the split-KV decode's in-kernel fold (paged_decode.cu): `count` zero-initialised ints of device
+// memory per device, registered by the caller like the error word; the kernels leave them zero.
+static int* g_decode_tickets[64] = {nullptr};
+static int64_t g_decode_ticket_count[64] = {0};
+
+int* decode_tickets(int64_t* count) {
+  int dev = 0;
+  *count = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  *count = g_decode_ticket_count[dev];
+  return g_decode_tickets[dev];
+}
+
 bool pdl_enabled() {
   const char* v = getenv("MOJO_B200_PDL");
   return !(v && v[0] == '0');
@@ -42,6 +55,16 @@ int mojo_b200_set_error_word(int* device_word) {
   MOJO_CUDA_OK(cudaGetDevice(&dev));
   MOJO_REQUIRE(dev >= 0 && dev < 64, MOJO_B200_EUNSUPPORTED, "set_error_word: device ordinal %d", dev);
   mojo::g_error_word[dev] = device_word;
+  return 0;
+}
+
+int mojo_b200_set_decode_tickets(int* device_words, int64_t count) {
+  int dev = 0;
+  MOJO_CUDA_OK(cudaGetDevice(&dev));
+  MOJO_REQUIRE(dev >= 0 && dev < 64, MOJO_B200_EUNSUPPORTED, "set_decode_tickets: device ordinal %d", dev);
+  MOJO_REQUIRE(count >= 0 && (device_words || count == 0), MOJO_B200_EINVAL, "set_decode_tickets: bad arguments");
+  mojo::g_decode_tickets[dev] = count > 0 ? device_words : nullptr;
+  mojo::g_decode_ticket_count[dev] = count > 0 ? count : 0;
   return 0;
 }
 

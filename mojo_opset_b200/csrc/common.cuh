@@ -21,6 +21,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 char* last_error_buffer();  // thread-local, defined in api.cu
 int fail(int code, const char* fmt, ...);
 int* error_word();  // the current device's registered error word (api.cu), or null
+int* decode_tickets(int64_t* count);  // the current device's registered split-KV arrival counters (api.cu), or null
 
 #define MOJO_REQUIRE(cond, code, ...)                 \
   do {                                                \

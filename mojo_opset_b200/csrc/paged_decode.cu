@@ -56,7 +56,26 @@ struct DecodeParams {
   // k < win_global; -1 = that window is not set (both -1: every key, MojoPagedDecodeGQA)
   int win_local, win_global;
   int* err;  // device error word or null (include/mojo_b200.h)
+  // split-KV: arrival counters (one per (sequence, kv head tile), zero between launches) - the last split of a group
+  // to arrive folds the group's partials itself; null = fold by paged_decode_reduce_kernel
+  int* tickets;
+  unsigned long long* trace;  // developer timeline (MOJO_DECODE_TRACE builds only, tools/decode_trace.py)
 };
+
+#ifdef MOJO_DECODE_TRACE
+// per CTA: [0] entry, [1] past pdl_wait, [2] first tile landed, [3] last tile consumed, [4] partial written,
+// [5] fold done (the group's last CTA only)  (globaltimer, ns)
+#define DTRACE(ev)                                                                                             \
+  do {                                                                                                         \
+    if (p.trace) {                                                                                             \
+      unsigned long long t__;                                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                                  \
+      p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (ev)] = t__;      \
+    }                                                                                                          \
+  } while (0)
+#else
+#define DTRACE(ev) do {} while (0)
+#endif
 
 __device__ __forceinline__ void split_tile_range(int seq_len, int num_splits, int split, int& tile_begin,
                                                  int& tile_end) {
@@ -106,9 +125,96 @@ __device__ __forceinline__ int q_head_of(const DecodeParams& p, int kvh, int j) 
 }
 
 // ======================================================================================================
+// split-KV fold inside the main kernel
+// ======================================================================================================
+// Timeline of the batch-1 / 32k-context launch (tools/decode_trace.py, 296 CTAs): the KV stream itself runs at 7.0 TB/s
+// (19 of the 31.7 us), but 5.6 us passed between the last partial and the next launch getting past its wait - the fold
+// kernel's launch hand-offs around ~3 us of dependent L2 round trips.  So the LAST split of a (sequence, kv head tile)
+// group to arrive (an arrival counter per group, reset by that CTA: zero between launches) folds the group's partials
+// itself: a warp per query head, every lane four features of the row, 16 partial rows requested per trip.
+template <typename T, int D>
+__device__ __forceinline__ void fold_group(const DecodeParams& p, int b, int kvh, int ht, int rows_valid, int tid) {
+  constexpr int F4 = D / 4;   // float4 chunks of a row: a lane takes chunk `lane`
+  constexpr int kBatch = 20;  // partial rows requested per trip (37 splits at batch 1 / 32k context: two trips)
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool has = lane < F4;
+  const int n = p.num_splits;  // <= 64 (checked by the launcher): a lane holds the (m, l) of splits lane, lane + 32
+  for (int r = warp; r < rows_valid; r += kConsumerWarps) {
+    const int hq = q_head_of(p, kvh, ht * 16 + r);
+    const int64_t base = ((int64_t)b * p.num_q_heads + hq) * n;
+    const float4* rows = reinterpret_cast<const float4*>(p.part_o + base * D) + lane;
+    // the (m, l) pairs and the first batch of rows are requested together: the rows do not depend on the weights
+    float2 ml0 = make_float2(-INFINITY, 0.f), ml1 = ml0;
+    if (lane < n) ml0 = __ldcg(&p.part_ml[base + lane]);
+    if (lane + 32 < n) ml1 = __ldcg(&p.part_ml[base + lane + 32]);
+    float4 v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u < n && has) v[u] = __ldcg(rows + (size_t)u * F4);
+    }
+    const float m = warp_max(fmaxf(ml0.x, ml1.x));
+    // an empty split (m = -inf) contributes nothing - its row is uninitialised memory and is never multiplied
+    const float f0 = ml0.x != -INFINITY ? exp2f(ml0.x - m) : 0.f;
+    const float f1 = ml1.x != -INFINITY ? exp2f(ml1.x - m) : 0.f;
+    const float l = warp_sum(f0 * ml0.y + f1 * ml1.y);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < n; s0 += kBatch) {
+      if (s0 > 0) {
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (s0 + u < n && has) v[u] = __ldcg(rows + (size_t)(s0 + u) * F4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int si = s0 + u;
+        const float fs = __shfl_sync(0xffffffffu, si < 32 ? f0 : f1, si & 31);
+        if (si < n && fs != 0.f) {
+          acc.x = fmaf(fs, v[u].x, acc.x);
+          acc.y = fmaf(fs, v[u].y, acc.y);
+          acc.z = fmaf(fs, v[u].z, acc.z);
+          acc.w = fmaf(fs, v[u].w, acc.w);
+        }
+      }
+    }
+    if (has) {
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      T* o = reinterpret_cast<T*>(p.out) + b * p.o_sb + hq * p.o_sh + lane * 4;
+      o[0] = DType<T>::from_f(acc.x * inv);
+      o[1] = DType<T>::from_f(acc.y * inv);
+      o[2] = DType<T>::from_f(acc.z * inv);
+      o[3] = DType<T>::from_f(acc.w * inv);
+    }
+  }
+}
+
+// Called by the CTA's first 128 threads once its partial is written: count the arrival, and fold if it was the last.
+template <typename T, int D>
+__device__ __forceinline__ void arrive_and_fold(const DecodeParams& p, int b, int kvh, int ht, int rows_valid) {
+  __shared__ int s_last;
+  __threadfence();  // this thread's partial stores are visible device-wide before the arrival is counted
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+  if (threadIdx.x == 0) {
+    int* tk = p.tickets + ((int64_t)b * gridDim.y + blockIdx.y);
+    const int last = atomicAdd(tk, 1) == p.num_splits - 1;
+    if (last) *tk = 0;  // every split of the group has arrived: the counter is ready for the next launch
+    s_last = last;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+  if (s_last) {
+    __threadfence();
+    fold_group<T, D>(p, b, kvh, ht, rows_valid, threadIdx.x);
+  }
+}
+
+// ======================================================================================================
 // fast path
 // ======================================================================================================
-template <typename T, int D, bool SPLIT_HALVES>
+// FOLD: the split-KV instantiation with the in-kernel fold above (the single-split instantiation - the cfg2 / cfg4
+// serving shapes at 1.00 of the HBM peak - carries none of that code: with it inlined the kernel measured 1 % slower)
+template <typename T, int D, bool SPLIT_HALVES, bool FOLD>
 __global__ void __launch_bounds__(kDecodeThreads, 2)
 paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_constant__ CUtensorMap v_map,
                         const DecodeParams p) {
@@ -131,6 +237,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DTRACE(0);
   // prologue that touches no other kernel's data (PDL: runs while the previous kernel drains)
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -145,6 +252,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
   }
   pdl_wait();
   pdl_trigger();
+  if (threadIdx.x == 0) DTRACE(1);
   const int seq_len = p.seq_lens[b];
   const int rows_valid = min(16, p.group - ht * 16);  // query heads in this tile
   // the reference raises ValueError for a row with keys but no first block (attention.py:186-187): flag it
@@ -168,6 +276,9 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
       } else if (d == 0) {
         p.part_ml[((int64_t)b * p.num_q_heads + hq) * p.num_splits + split] = make_float2(-INFINITY, 0.f);
       }
+    }
+    if constexpr (FOLD) {
+      if (threadIdx.x < kConsumerWarps * 32) arrive_and_fold<T, D>(p, b, kvh, ht, rows_valid);
     }
     return;
   }
@@ -270,6 +381,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
     const uint32_t sk_a = smem_u32(sk), sv_a = smem_u32(sv);
 
     mbar_wait(&full[stage], phase);
+    if (it == 0 && threadIdx.x == 0) DTRACE(2);
 
     if (valid < kTile) {
       // Tail tile: slots past the end of the sequence hold stale shared memory or uninitialised cache
@@ -361,6 +473,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
     if (lane == 0) mbar_arrive(&empty[stage]);
   }
 
+  if (threadIdx.x == 0) DTRACE(3);
   // -------------------------------------------------------------------- merge the four warps
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
@@ -408,6 +521,11 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
       p.part_o[slot * D + d] = acc;
       if (d == 0) p.part_ml[slot] = make_float2(m, l);
     }
+  }
+  if (threadIdx.x == 0) DTRACE(4);
+  if constexpr (FOLD) {
+    arrive_and_fold<T, D>(p, b, kvh, ht, rows_valid);
+    if (threadIdx.x == 0) DTRACE(5);
   }
 }
 
@@ -719,6 +837,21 @@ static int paged_decode_impl(
   p.scale = softmax_scale; p.interleave = gqa_interleave ? 1 : 0; p.num_splits = num_splits;
   p.win_local = win_local; p.win_global = win_global;
   p.err = error_word();
+#ifdef MOJO_DECODE_TRACE
+  if (const char* tp = getenv("MOJO_B200_DECODE_TRACE_PTR")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
+#endif
+  if (fast && num_splits > 1 && num_splits <= 64 && env_int("MOJO_B200_DECODE_FOLD", 1) != 0) {
+    // in-kernel fold: needs the registered, zero-between-launches arrival counters (mojo_b200_set_decode_tickets);
+    // consecutive launches rotate over disjoint slices, so launches in flight on different streams do not share one
+    int64_t count = 0;
+    int* words = decode_tickets(&count);
+    const int64_t groups = (int64_t)batch * num_kv_heads * head_tiles;
+    if (words && count >= groups) {
+      static unsigned launch_seq = 0;
+      const int64_t slices = count / groups < 16 ? count / groups : 16;
+      p.tickets = words + (int64_t)(launch_seq++ % (unsigned)slices) * groups;
+    }
+  }
 
   if (num_splits > 1) {
     const size_t need = mojo_b200_paged_decode_workspace_bytes(batch, num_q_heads, head_dim, num_splits);
@@ -759,7 +892,7 @@ static int paged_decode_impl(
 
 #define LAUNCH_FAST(TT, DD, SH)                                                                          \
   do {                                                                                                   \
-    auto kern = paged_decode_mma_kernel<TT, DD, SH>;                                                     \
+    auto kern = p.tickets ? paged_decode_mma_kernel<TT, DD, SH, true> : paged_decode_mma_kernel<TT, DD, SH, false>; \
     MOJO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     MOJO_CUDA_OK(launch_pdl(kern, grid, dim3(kDecodeThreads), smem, s, k_map, v_map, p));                \
   } while (0)
@@ -798,7 +931,7 @@ static int paged_decode_impl(
     if (int rc2 = check_launch("paged_decode_simt_kernel")) return rc2;
   }
 
-  if (num_splits > 1) {
+  if (num_splits > 1 && !p.tickets) {
     dim3 rgrid((unsigned)num_q_heads, (unsigned)batch);
     int rc = dispatch_dtype(dtype, [&](auto tag) {
       using TT = decltype(tag);

@@ -38,6 +38,8 @@ def _chain(ops, B=24, ctx=700, Hq=32, Hkv=8, D=128, bs=16, hidden=1024, inter=30
     d["table"], d["meta"] = table.to(DEV), meta.contiguous().to(DEV)
     d["lens"] = torch.full((B,), ctx, dtype=torch.int32, device=DEV)
     norm = ops.MojoResidualAddRMSNorm(hidden, eps=1e-6, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():  # (the op allocates its weight like the reference does: uninitialised memory)
+        norm.weight.copy_(1 + 0.1 * torch.randn(hidden, generator=g))
     rope, store, decode, swiglu = ops.MojoApplyRoPE(), ops.MojoStorePagedKVCache(), ops.MojoPagedDecodeGQA(), ops.MojoSwiGLU()
 
     def step():
@@ -67,11 +69,12 @@ def test_chain_with_pdl_equals_plain_stream_order(ops, monkeypatch):
     for _ in range(25):
         graph.replay()
     torch.cuda.synchronize()
-    for got in outs:
-        for a, b in zip(got, ref):
-            assert torch.equal(a, b), "a replay with programmatic dependent launch differs from plain stream order"
+    for k, got in enumerate(outs):
+        for name, a, b in zip("yroa", got, ref):
+            assert torch.equal(a, b), (f"step {k} of the replayed graph, output {name}: {int((a != b).sum())} of {a.numel()} "
+                                       "elements differ from plain stream order")
     for _ in range(25):  # eager, back to back
         got = step()
     torch.cuda.synchronize()
-    for a, b in zip(got, ref):
-        assert torch.equal(a, b)
+    for name, a, b in zip("yroa", got, ref):
+        assert torch.equal(a, b), f"eager, output {name}: {int((a != b).sum())} of {a.numel()} elements differ"

@@ -106,3 +106,45 @@ def test_unmapped_first_block_raises_value_error_like_the_reference(ops):
     ops.MojoPagedPrefillGQA()(qp, kc, vc, cu, table, max_q_len=20)
     with pytest.raises(ValueError, match="Paged prefill requires a valid block table"):
         m.check_device_errors()
+
+
+@pytest.mark.parametrize("splits", [2, 5, 37])
+def test_split_kv_fold_in_kernel_matches_fold_kernel_and_oracle(ops, splits, monkeypatch):
+    """Split-KV decode: the last split of a (sequence, kv head) group to arrive folds the group's partials inside the
+    main kernel (arrival counters registered with `mojo_b200_set_decode_tickets`).  Both fold paths must agree with the
+    oracle on a ragged batch with empty sequences and empty splits, over repeated launches (the counters must be back
+    at zero after every launch) and for more rows than one 16-head tile."""
+    from mojo_opset_b200 import _lib
+    from oracle import golden
+
+    g = torch.Generator().manual_seed(splits)
+    Hq, Hkv, D, bs = 40, 2, 128, 16  # group 20: two head tiles per kv head
+    lens = [2500, 0, 70, 1, 1023, 64, 2400]
+    B, max_len = len(lens), 2560
+    nblk = max_len // bs
+    nb = B * nblk + 3
+    kc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16).to(DEV)
+    vc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16).to(DEV)
+    q = torch.randn(B, Hq, D, generator=g).to(torch.bfloat16).to(DEV)
+    table = torch.full((B, nblk), -1, dtype=torch.int32)
+    perm = torch.randperm(nb, generator=g)
+    at = 0
+    for i, n in enumerate(lens):
+        need = (n + bs - 1) // bs
+        table[i, :need] = perm[at:at + need].to(torch.int32)
+        at += need
+    table, seq = table.to(DEV), torch.tensor(lens, dtype=torch.int32, device=DEV)
+    ref = golden.paged_decode_gqa(q, kc, vc, seq, table)
+    op = ops.MojoPagedDecodeGQA()
+    monkeypatch.setenv("MOJO_B200_DECODE_SPLITS", str(splits))
+    outs = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("MOJO_B200_DECODE_FOLD", fold)
+        for _ in range(3):
+            outs[fold] = op(q, kc, vc, seq, table, max_total_seq_len=max_len)
+        torch.testing.assert_close(outs[fold].float(), ref.float(), atol=2e-2, rtol=2e-2)
+        assert not outs[fold][1].float().abs().sum().item()  # the empty sequence reads as zeros
+    torch.testing.assert_close(outs["1"].float(), outs["0"].float(), atol=4e-3, rtol=1e-2)  # summation order only
+    torch.cuda.synchronize()
+    tickets = _lib._decode_tickets[torch.cuda.current_device()]
+    assert int(tickets.abs().sum().item()) == 0, "arrival counters must be zero between launches"
