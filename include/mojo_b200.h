@@ -286,7 +286,11 @@ MOJO_B200_API int mojo_b200_sdpa_masked(const void* query, const void* key, cons
  * once there are two 128-row blocks), partial tile rows pushed over NVLink into the tile owner's workspace as
  * self-validating 16-byte lines (3 payload words + the call's epoch, one 128-bit system-scope store each), fp32
  * reduction in rank order (bit-identical on all ranks), reduced lines broadcast to every rank.  world == 1 is a plain
- * GEMM (no workspace).  Launched with programmatic stream serialization (MOJO_B200_PDL=0 turns it off).
+ * GEMM (no workspace).  Launched with programmatic stream serialization (MOJO_B200_PDL=0 turns it off): the kernel
+ * requests its first tiles of `weight` while the previous kernel of the stream is still draining and waits for that
+ * kernel before it reads x / bias - so `weight` must not be written by the kernel launched immediately before this
+ * call (model weights never are; a just-in-time dequantisation into `weight` needs MOJO_B200_PDL=0 or any kernel in
+ * between).
  *
  * The workspace is "symmetric": every rank allocates the same number of bytes with mojo_b200_symm_alloc
  * (cudaMalloc, zero-filled), exports it (64-byte CUDA IPC handle), exchanges handles out of band (the host side
