@@ -69,8 +69,9 @@ def test_gemm_leading_dims_and_strided_rows(F, golden):
 
 @pytest.mark.parametrize("mode", ["one", "two"])  # one-shot (push to all, local reduce) / two-shot (owner reduces)
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("m,n,k_local", [(256, 1024, 256), (40, 384, 128), (300, 520, 72)])
-def test_virtual_ranks_protocol(F, golden, world, m, n, k_local, mode, monkeypatch):
+@pytest.mark.parametrize("m,n,k_local,dtype", [(256, 1024, 256, torch.bfloat16), (40, 384, 128, torch.bfloat16),
+                                               (300, 520, 72, torch.bfloat16), (130, 264, 136, torch.float16)])
+def test_virtual_ranks_protocol(F, golden, world, m, n, k_local, dtype, mode, monkeypatch):
     from mojo_opset_b200.comm import LocalRanks
 
     monkeypatch.setenv("MOJO_B200_GAR_MODE", mode)
@@ -79,9 +80,9 @@ def test_virtual_ranks_protocol(F, golden, world, m, n, k_local, mode, monkeypat
     ranks = LocalRanks(world, nbytes)
     try:
         for call in range(4):  # both parities twice
-            xs = [torch.randn(m, k_local, generator=g).to(torch.bfloat16) for _ in range(world)]
-            ws = [torch.randn(n, k_local, generator=g).to(torch.bfloat16) for _ in range(world)]
-            bs = [torch.randn(n, generator=g).to(torch.bfloat16) for _ in range(world)]
+            xs = [torch.randn(m, k_local, generator=g).to(dtype) for _ in range(world)]
+            ws = [torch.randn(n, k_local, generator=g).to(dtype) for _ in range(world)]
+            bs = [torch.randn(n, generator=g).to(dtype) for _ in range(world)]
             ref = golden.gemm_allreduce_emulated(xs, ws, bs)
             xd, wd, bd = ([t.to(DEV) for t in ts] for ts in (xs, ws, bs))
             torch.cuda.synchronize()

@@ -108,8 +108,9 @@ def test_unmapped_first_block_raises_value_error_like_the_reference(ops):
         m.check_device_errors()
 
 
+@pytest.mark.parametrize("head_dim,dtype", [(128, torch.bfloat16), (64, torch.float16)])
 @pytest.mark.parametrize("splits", [2, 5, 37])
-def test_split_kv_fold_in_kernel_matches_fold_kernel_and_oracle(ops, splits, monkeypatch):
+def test_split_kv_fold_in_kernel_matches_fold_kernel_and_oracle(ops, splits, head_dim, dtype, monkeypatch):
     """Split-KV decode: the last split of a (sequence, kv head) group to arrive folds the group's partials inside the
     main kernel (arrival counters registered with `mojo_b200_set_decode_tickets`).  Both fold paths must agree with the
     oracle on a ragged batch with empty sequences and empty splits, over repeated launches (the counters must be back
@@ -118,14 +119,14 @@ def test_split_kv_fold_in_kernel_matches_fold_kernel_and_oracle(ops, splits, mon
     from oracle import golden
 
     g = torch.Generator().manual_seed(splits)
-    Hq, Hkv, D, bs = 40, 2, 128, 16  # group 20: two head tiles per kv head
+    Hq, Hkv, D, bs = 40, 2, head_dim, 16  # group 20: two head tiles per kv head
     lens = [2500, 0, 70, 1, 1023, 64, 2400]
     B, max_len = len(lens), 2560
     nblk = max_len // bs
     nb = B * nblk + 3
-    kc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16).to(DEV)
-    vc = torch.randn(nb, Hkv, bs, D, generator=g).to(torch.bfloat16).to(DEV)
-    q = torch.randn(B, Hq, D, generator=g).to(torch.bfloat16).to(DEV)
+    kc = torch.randn(nb, Hkv, bs, D, generator=g).to(dtype).to(DEV)
+    vc = torch.randn(nb, Hkv, bs, D, generator=g).to(dtype).to(DEV)
+    q = torch.randn(B, Hq, D, generator=g).to(dtype).to(DEV)
     table = torch.full((B, nblk), -1, dtype=torch.int32)
     perm = torch.randperm(nb, generator=g)
     at = 0
