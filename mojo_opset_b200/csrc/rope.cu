@@ -93,9 +93,13 @@ __global__ void __launch_bounds__(256) apply_rope_kernel(const RopeArgs a) {
 // costs registers, hence resident warps, and measured slower (tools/microbench/stream3.cu).  The partner slice
 // is loaded by two threads of the same warp instruction (one L1 request).  No integer division in the loop.
 // Requires SLICES = head_dim / VEC to be a power of two <= 32.
-template <typename T, typename C, int VEC, bool ROUND_T, int SLICES>
-__global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs a) {
-  constexpr int HSLOTS = 256 / SLICES;
+// THREADS / TRIPS: 256 threads with three head rows in flight per thread for decode-sized launches (latency: 2.0 us at
+// 64 tokens); 128 threads with five for prefill-sized ones - ncu: ~21 instructions per element at 256 threads, most of
+// them per-token set-up (cos / sin conversion, 64-bit address arithmetic) amortised over only 24 elements per thread;
+// at 128 threads a thread owns 40 (T = 8192: 35.2 -> 32.6 us = 0.83 of the HBM peak; 64 threads: no better)
+template <typename T, typename C, int VEC, bool ROUND_T, int SLICES, int THREADS, int TRIPS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) apply_rope_slice_kernel(const RopeArgs a) {
+  constexpr int HSLOTS = THREADS / SLICES;
   const int sl = threadIdx.x % SLICES, hs = threadIdx.x / SLICES;
   pdl_wait();
   pdl_trigger();
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs
   // The first kRopeTrips head rows of a thread are all requested before any is rotated (one dependent load per trip made
   // the kernel latency-bound: 0.71 of the HBM peak at T = 8192), and the partner slice comes from the partner lane
   // (same head, rope_dim/2 elements away = a fixed lane distance inside the warp) by shuffle instead of a second load.
-  constexpr int kRopeTrips = 3;
+  constexpr int kRopeTrips = TRIPS;
   constexpr int kWords = VEC * (int)sizeof(T) / 4;
   static_assert(kWords >= 1, "slices are at least one word");
   const int partner_lane = (int)(threadIdx.x & 31u) + (second ? -(half / VEC) : (half / VEC));
@@ -238,14 +242,23 @@ __global__ void __launch_bounds__(256, 4) apply_rope_slice_kernel(const RopeArgs
 template <typename T, typename C, int VEC, bool ROUND_T>
 static bool launch_rope_fast(const RopeArgs& a, int64_t tokens, cudaStream_t s) {
   if (a.head_dim % VEC) return false;
-  const int64_t cap = (int64_t)kNumSMs * 4 * 3;
+  const bool big = tokens >= 1024;  // prefill-sized: fewer, busier threads per token
+  const int threads = big ? 128 : 256;
+  const int64_t cap = (int64_t)kNumSMs * (1024 / threads) * 3;
   const unsigned grid = (unsigned)(tokens < cap ? tokens : cap);
+#define ROPE_FAST(SL)                                                                                                  \
+  do {                                                                                                                 \
+    if (big) launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, SL, 128, 5>, dim3(grid), dim3(128), 0, s, a);      \
+    else launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, SL, 256, 3>, dim3(grid), dim3(256), 0, s, a);          \
+    return true;                                                                                                       \
+  } while (0)
   switch (a.head_dim / VEC) {
-    case 8: launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, 8>, dim3(grid), dim3(256), 0, s, a); return true;
-    case 16: launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, 16>, dim3(grid), dim3(256), 0, s, a); return true;
-    case 32: launch_pdl(apply_rope_slice_kernel<T, C, VEC, ROUND_T, 32>, dim3(grid), dim3(256), 0, s, a); return true;
+    case 8: ROPE_FAST(8);
+    case 16: ROPE_FAST(16);
+    case 32: ROPE_FAST(32);
     default: return false;
   }
+#undef ROPE_FAST
 }
 
 template <typename T, typename C, bool ROUND_T>
