@@ -72,9 +72,12 @@ template <typename T> __device__ __forceinline__ Row8 pack8(const float (&f)[8])
 
 // LPH = lanes per head = D / 8; C = cos/sin element type (float or T); NORM: apply the per-head RMSNorm
 constexpr int kNrsThreads = 128;
+#ifndef MOJO_NRS_MIN_CTAS
+#define MOJO_NRS_MIN_CTAS 6  // 80 registers, no spill: T = 8192 44.9 -> 42.5 us (7 and 8 spill and lose at decode sizes)
+#endif
 
 template <typename T, typename C, int LPH, bool NORM>
-__global__ void __launch_bounds__(kNrsThreads, 5) norm_rope_store_kernel(const NrsArgs a) {
+__global__ void __launch_bounds__(kNrsThreads, MOJO_NRS_MIN_CTAS) norm_rope_store_kernel(const NrsArgs a) {
   constexpr int D = LPH * 8;
   constexpr int HSLOTS = kNrsThreads / LPH;
   __shared__ int64_t s_slot[2];
