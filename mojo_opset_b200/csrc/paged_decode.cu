@@ -23,6 +23,7 @@
 // Golden rounding points (reference attention.py:217-228) reproduced: for 16-bit inputs the score is rounded
 // to the input dtype after the dot product and again after scaling; probabilities are rounded to the input
 // dtype before the PV product; everything else is fp32.
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -847,9 +848,9 @@ static int paged_decode_impl(
     int* words = decode_tickets(&count);
     const int64_t groups = (int64_t)batch * num_kv_heads * head_tiles;
     if (words && count >= groups) {
-      static unsigned launch_seq = 0;
+      static std::atomic<unsigned> launch_seq{0};  // (host threads may launch concurrently)
       const int64_t slices = count / groups < 16 ? count / groups : 16;
-      p.tickets = words + (int64_t)(launch_seq++ % (unsigned)slices) * groups;
+      p.tickets = words + (int64_t)(launch_seq.fetch_add(1, std::memory_order_relaxed) % (unsigned)slices) * groups;
     }
   }
 
