@@ -879,6 +879,16 @@ def run_tp_cfg4(m, dev, rank, world, peaks, args, barrier, max_over_ranks):
         "decode_us_max_rank": dec_ms * 1e3, "decode_bytes_per_rank": kv_bytes, "decode_gbs_per_rank": gbs,
         "decode_frac_of_measured_hbm": gbs / peaks["hbm_gbs"],
         "allreduce_bytes": B * hidden * 2,
+        # roofline of the fused compute + collective kernel (B200_PROFILING.md): the slower of FLOPs / measured GEMM peak
+        # and the bytes that must cross NVLink (two-shot all-reduce payload per GPU and direction) / 770 GB/s measured
+        "fused_roofline": (lambda flops, nvl: {
+            "gemm_flops": flops, "gemm_floor_us": flops / (peaks["bf16_tflops"] * 1e6),
+            "nvlink_bytes_per_gpu_per_direction": nvl, "nvlink_gbs": 770.0, "nvlink_floor_us": nvl / 770e3,
+            "floor_us": max(flops / (peaks["bf16_tflops"] * 1e6), nvl / 770e3),
+            "fused_us_in_step": (ms_fused - ms_attn) * 1e3,
+            "frac": max(flops / (peaks["bf16_tflops"] * 1e6), nvl / 770e3) / max((ms_fused - ms_attn) * 1e3, 1e-9),
+            "frac_cublas_nccl": max(flops / (peaks["bf16_tflops"] * 1e6), nvl / 770e3) / max((ms_unfused - ms_attn) * 1e3, 1e-9),
+        })(2.0 * B * hidden * hq_l * D, 2.0 * (world - 1) / world * B * hidden * 2),
         "parity": {"ok": ok, "decode_rel_err_vs_oracle": err_o, "fused_rel_err_vs_oracle": err_y,
                    "fused_rel_tol": tol, "decode_rel_tol": 1.5e-2, "ranks_bit_identical": same, "notes": notes},
         "timing": "CUDA events, the four variants interleaved, median of 5 regions of K steps each, max over ranks",
