@@ -46,7 +46,9 @@ def _tol(k):
                                     (300, 1000, 8), (128, 128, 4104)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("with_bias", [False, True])
-def test_gemm_single_rank(F, golden, m, n, k, dtype, with_bias):
+@pytest.mark.parametrize("pair", ["0", "1"], ids=["single-cta", "cta-pairs"])  # (the launcher picks by shape; force both)
+def test_gemm_single_rank(F, golden, m, n, k, dtype, with_bias, pair, monkeypatch):
+    monkeypatch.setenv("MOJO_B200_GAR_PAIR", pair)
     g = torch.Generator().manual_seed(m * 7 + n + k)
     x = torch.randn(m, k, generator=g).to(dtype)
     w = torch.randn(n, k, generator=g).to(dtype)
@@ -71,10 +73,12 @@ def test_gemm_leading_dims_and_strided_rows(F, golden):
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("m,n,k_local,dtype", [(256, 1024, 256, torch.bfloat16), (40, 384, 128, torch.bfloat16),
                                                (300, 520, 72, torch.bfloat16), (130, 264, 136, torch.float16)])
-def test_virtual_ranks_protocol(F, golden, world, m, n, k_local, dtype, mode, monkeypatch):
+@pytest.mark.parametrize("pair", ["0", "1"], ids=["single-cta", "cta-pairs"])
+def test_virtual_ranks_protocol(F, golden, world, m, n, k_local, dtype, mode, pair, monkeypatch):
     from mojo_opset_b200.comm import LocalRanks
 
     monkeypatch.setenv("MOJO_B200_GAR_MODE", mode)
+    monkeypatch.setenv("MOJO_B200_GAR_PAIR", pair)
     g = torch.Generator().manual_seed(world * 1000 + m)
     nbytes = F.gemm_allreduce_workspace_bytes(m, n, world)
     ranks = LocalRanks(world, nbytes)
