@@ -773,11 +773,15 @@ extern "C" int mojo_b200_gemm_allreduce(const void* x, const void* weight, const
     }
   }
 
-  // CTA pairs (cta_group::2, 256 x 128 work items) once there are at least two 128-row blocks to pair up.  Measured,
-  // own GEMM, n 8192 (single CTAs / pairs): m 256 k 1024 8.2 / 8.7 us; m 256 k 4096 22.3 / 22.2; m 512 k 4096 41.0 /
-  // 38.9; m 8192 k 1024 143 / 134 - pairs lose the shallow decode-sized case stand-alone by the cluster set-up, which
-  // the PDL prologue hides inside a layer step.  MOJO_B200_GAR_PAIR = 0 forces single CTAs.
-  const bool pair = p.tiles_m >= 2 && env_flag("MOJO_B200_GAR_PAIR", 1) && pair_clusters_fit();
+  // CTA pairs (cta_group::2, 256 x 128 work items) once there are at least two 128-row blocks to pair up - except for
+  // the shallow, decode-sized case (fewer than four row blocks and k <= 1024), where the cluster set-up and the slower
+  // peer-served operand reads cost more than the lower L2 traffic saves.  Measured, n 8192 (single CTAs / pairs): own
+  // GEMM m 256 k 1024 8.2 / 8.7 us; m 256 k 4096 22.3 / 22.2; m 512 k 4096 41.0 / 38.9; m 8192 k 1024 143 / 134; inside
+  // the TP8 cfg4 layer step (k 1024) fused kernel 36.8 / 38.5 us.  MOJO_B200_GAR_PAIR = 0 / 1 forces a mode.
+  const int k_blocks_host = (int)((k + kBK - 1) / kBK);
+  const bool pair_pays = p.tiles_m >= 4 || k_blocks_host > 16;
+  const char* pair_env = getenv("MOJO_B200_GAR_PAIR");
+  const bool pair = p.tiles_m >= 2 && ((pair_env && *pair_env) ? atoi(pair_env) != 0 : pair_pays) && pair_clusters_fit();
   p.n_pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
 
   CUtensorMap a_map, b_map;

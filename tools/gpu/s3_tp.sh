@@ -15,9 +15,7 @@ for v in "$@"; do
     nopair) run nopair MOJO_B200_GAR_PAIR=0;;
     two) run two MOJO_B200_GAR_MODE=two;;
     one) run one MOJO_B200_GAR_MODE=one;;
+    nobench) exit 0;;
   esac
 done
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 tools/bench_gemm_allreduce.py --check --steps 20 --warmup 5 2>gpurun_out/s3_gar_n$N.err | tail -3 | tee gpurun_out/s3_gar_n$N.txt | cut -c1-900
-for tok in 16 64; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29537 tools/bench_gemm_allreduce.py --tokens $tok --steps 20 --warmup 5 2>>gpurun_out/s3_gar_n$N.err | tail -1 | tee -a gpurun_out/s3_gar_n$N.txt | cut -c1-700
-done
