@@ -205,3 +205,37 @@ def test_ctypes_signatures_match_the_header():
         assert declared == bound, f"{name}: header {declared} != ctypes {bound}"
         want_ret = "ptr" if "*" in ret else kind_of(ret.strip() + " x")
         assert kinds.get(restype, "ptr") == want_ret, f"{name}: return type"
+
+
+def test_every_pdl_launched_kernel_waits_before_touching_memory():
+    """Source lint for programmatic dependent launch (csrc/common.cuh): a kernel launched through `launch_pdl` (or with
+    the programmatic-serialization attribute) may start while its predecessor is still running, so it must execute
+    `pdl_wait()` (griddepcontrol.wait).  Every `__global__` kernel of a file that uses PDL must therefore either contain
+    `pdl_wait()` or be launched with plain `<<<...>>>` only."""
+    import re
+
+    csrc = os.path.join(ROOT, "mojo_opset_b200", "csrc")
+    checked = 0
+    for fname in sorted(os.listdir(csrc)):
+        if not fname.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, fname)).read()
+        if "launch_pdl(" not in src and "ProgrammaticStreamSerialization" not in src:
+            continue
+        for m in re.finditer(r"__global__\s+void\s+(?:__launch_bounds__\s*\([^)]*\)\s*)?(\w+)\s*\(", src):
+            name = m.group(1)
+            start = src.index("{", m.end())
+            depth, i = 0, start
+            while True:  # the kernel's body by brace matching
+                depth += {"{": 1, "}": -1}.get(src[i], 0)
+                if depth == 0:
+                    break
+                i += 1
+            body = src[start:i]
+            plain = re.search(r"\b%s\s*(<[^;]*?>)?\s*<<<" % re.escape(name), src) is not None
+            via_pdl = re.search(r"launch_pdl\(\s*%s\b" % re.escape(name), src) is not None or \
+                re.search(r"=\s*(\w+\s*\?\s*)?%s\s*<" % re.escape(name), src) is not None  # `auto kern = name<...>`
+            if via_pdl or not plain:
+                assert "pdl_wait()" in body, f"{fname}: kernel {name} is launched with PDL but never calls pdl_wait()"
+                checked += 1
+    assert checked >= 9, checked
