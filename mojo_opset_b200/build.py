@@ -75,7 +75,42 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs or force or _stale(LIB_PATH, objects):
         run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objects,
              "-cudart", "static", "-Xlinker", "--exclude-libs,ALL"])
+    _write_kernel_sass()
     return LIB_PATH
+
+
+# The headline decode kernel (cfg2: bf16, head_dim 128, split-halves layout, single split).  bench.py accepts an ncu
+# DRAM-traffic capture (profiles/decode_traffic.json) only for the kernel it runs: same sources, or - when a source file
+# changed without changing this kernel - the same machine code, which is what this hash pins.
+DECODE_KERNEL_SYMBOL = "_ZN4mojo23paged_decode_mma_kernelI13__nv_bfloat16Li128ELb1ELb0EEEv14CUtensorMap_stS2_NS_12DecodeParamsE"
+KERNEL_SASS_PATH = os.path.join(PKG_DIR, "kernel_sass.json")
+
+
+def kernel_sass_sha256(obj: str, symbol: str):
+    """sha256 over the instruction lines (address, mnemonic, operands, encoding) of one kernel in an object file."""
+    import hashlib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(obj):
+        return None
+    res = subprocess.run([cuobjdump, "-sass", "-fun", symbol, obj], capture_output=True, text=True)
+    lines = [ln.strip() for ln in res.stdout.splitlines() if ln.lstrip().startswith("/*")]
+    if res.returncode != 0 or len(lines) < 100:
+        return None
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()
+
+
+def _write_kernel_sass():
+    import json
+
+    obj = os.path.join(OBJ_DIR, "paged_decode.o")
+    if os.path.exists(KERNEL_SASS_PATH) and os.path.exists(obj) and os.path.getmtime(KERNEL_SASS_PATH) >= os.path.getmtime(obj):
+        return
+    digest = kernel_sass_sha256(obj, DECODE_KERNEL_SYMBOL)
+    if digest:
+        with open(KERNEL_SASS_PATH, "w") as f:
+            json.dump({"paged_decode_mma_kernel<bf16, 128, split-halves, single split>":
+                       {"symbol": DECODE_KERNEL_SYMBOL, "sass_sha256": digest}}, f, indent=1)
 
 
 if __name__ == "__main__":

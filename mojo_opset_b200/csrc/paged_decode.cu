@@ -279,6 +279,10 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap k_map, const __grid_
       }
     }
     if constexpr (FOLD) {
+      // every thread of the CTA (the producer warp included) may have written one of the (m, l) pairs above: all of
+      // them are ordered before the arrival is counted by the first 128
+      __threadfence();
+      __syncthreads();
       if (threadIdx.x < kConsumerWarps * 32) arrive_and_fold<T, D>(p, b, kvh, ht, rows_valid);
     }
     return;

@@ -239,3 +239,32 @@ def test_every_pdl_launched_kernel_waits_before_touching_memory():
                 assert "pdl_wait()" in body, f"{fname}: kernel {name} is launched with PDL but never calls pdl_wait()"
                 checked += 1
     assert checked >= 9, checked
+
+
+def test_decode_traffic_capture_is_bound_to_the_measured_kernel(monkeypatch, tmp_path):
+    """bench.py takes `roofline.traffic` from an ncu capture only if it was taken on the decode kernel it runs: the same
+    sources, or - after a change elsewhere in the file - the same machine code of the measured instantiation (the SASS
+    hash `mojo_opset_b200/build.py` pins at build time).  Anything else is refused."""
+    import json
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from mojo_opset_b200 import build
+
+    capture = os.path.join(ROOT, "profiles", "decode_traffic.json")
+    if not os.path.exists(capture) or not os.path.exists(build.KERNEL_SASS_PATH):
+        pytest.skip("no capture / no built kernel hash in this tree")
+    with open(capture) as f:
+        t = json.load(f)
+    traffic, source = bench.load_decode_traffic()
+    assert traffic == t["dram_bytes_per_launch"], source          # the committed capture matches the committed tree
+    monkeypatch.setattr(bench, "sources_sha256", lambda paths=bench.DECODE_SOURCES: "0" * 64)
+    traffic, source = bench.load_decode_traffic()                 # other sources, same SASS: accepted, and it says so
+    if t.get("kernel_sass_sha256"):
+        assert traffic == t["dram_bytes_per_launch"] and "SASS is identical" in source
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))             # no built hash next to the sources: refused
+    os.makedirs(tmp_path / "profiles")
+    with open(tmp_path / "profiles" / "decode_traffic.json", "w") as f:
+        json.dump(t, f)
+    traffic, source = bench.load_decode_traffic()
+    assert traffic is None and "refused" in source

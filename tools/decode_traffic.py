@@ -20,6 +20,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
+from mojo_opset_b200 import build  # noqa: E402
 
 
 def main():
@@ -52,6 +53,7 @@ def main():
         "algorithmic_bytes": bench.decode_bytes(cfg["batch"], cfg["ctx"], cfg["hq"], cfg["hkv"], cfg["d"], cfg["bs"]),
         "gpu_time_us_under_ncu": metric("gpu__time_duration.sum"),
         "source_sha256": bench.sources_sha256(),
+        "kernel_sass_sha256": build.kernel_sass_sha256(os.path.join(build.OBJ_DIR, "paged_decode.o"), build.DECODE_KERNEL_SYMBOL),
         "commit": subprocess.run(["git", "-C", ROOT, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip(),
     }
     if os.path.abspath(raw) != os.path.abspath(keep):
